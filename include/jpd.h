@@ -1,0 +1,144 @@
+/* jpd.h -- C ABI of libjpd.so, the B200 (sm_100a) batched Jacobi eigensolver.
+ *
+ * Drop-in boundary for ONE path of jewettaij/jacobi_pd:
+ *
+ *   int Jacobi<Scalar,Vector,Matrix,ConstMatrix>::Diagonalize(
+ *         ConstMatrix mat, Vector eval, Matrix evec,
+ *         SortCriteria sort_criteria = SORT_DECREASING_EVALS,
+ *         bool calc_evecs = true, int max_num_sweeps = 50);
+ *                                   (reference: include/jacobi_pd.hpp:76-81, impl :159-220)
+ *
+ * The reference is a header-only C++ template, it has no FFI of its own; these entry
+ * points are what a binding for that member function would call.  Plain pointers and
+ * sizes only, no C++ or torch types.  INTEGRATION.md shows the reference-side stub.
+ *
+ * Semantics kept from the reference (per matrix):
+ *   - only mat[i][j], j >= i is read                         (jacobi_pd.hpp:167-171)
+ *   - eigenvector k is ROW k of evecs                        (jacobi_pd.hpp:69)
+ *   - sort_criteria values 0..4 = DO_NOT_SORT, SORT_DECREASING_EVALS,
+ *     SORT_INCREASING_EVALS, SORT_DECREASING_ABS_EVALS, SORT_INCREASING_ABS_EVALS;
+ *     ties resolve as the reference's selection sort does   (jacobi_pd.hpp:56-62, 477-508)
+ *   - n_iters[b] > 0  : converged (rotations performed + 1)
+ *     n_iters[b] == 0 : max_num_sweeps exhausted and n > 1   (jacobi_pd.hpp:214-219)
+ * Deliberate deviations (DESIGN.md "deviations"): pair order is a static round-robin, not
+ * max-pivot, so rotation counts and the DO_NOT_SORT order differ for n > 2; when
+ * calc_evecs == 0 the evecs buffer may be NULL and is never touched.
+ *
+ * Layouts (argument `layout`):
+ *   JPD_LAYOUT_AOS (0)  mat[b*n*n + i*n + j]   evals[b*n + k]   evecs[b*n*n + k*n + v]
+ *   JPD_LAYOUT_SOA (1)  mat[(i*n+j)*batch + b] evals[k*batch+b] evecs[(k*n+v)*batch + b]
+ *                       (interleaved structure of arrays: coalesced for thread-per-matrix;
+ *                        lower-triangle planes of `mat` are never read)
+ *
+ * Return value of every function: 0 on success, negative JPD_ERR_* otherwise.  Nothing
+ * throws.  There is NO CPU fallback: without a CUDA device the calls fail with
+ * JPD_ERR_CUDA.
+ */
+#ifndef JPD_H_
+#define JPD_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JPD_LAYOUT_AOS 0
+#define JPD_LAYOUT_SOA 1
+
+#define JPD_DO_NOT_SORT 0
+#define JPD_SORT_DECREASING_EVALS 1
+#define JPD_SORT_INCREASING_EVALS 2
+#define JPD_SORT_DECREASING_ABS_EVALS 3
+#define JPD_SORT_INCREASING_ABS_EVALS 4
+
+#define JPD_OK 0
+#define JPD_ERR_INVALID_ARG (-1)
+#define JPD_ERR_UNSUPPORTED (-2)
+#define JPD_ERR_CUDA (-3)
+#define JPD_ERR_ALLOC (-4)
+
+#define JPD_MAX_N 1024
+
+#if defined(__GNUC__)
+#define JPD_API __attribute__((visibility("default")))
+#else
+#define JPD_API
+#endif
+
+/* ---- device-resident batches (the hot path) --------------------------------------
+ * All pointers are DEVICE pointers on the current device; the call is asynchronous on
+ * `cuda_stream` (a cudaStream_t, NULL = default stream).  d_evecs may be NULL iff
+ * calc_evecs == 0; d_n_iters may be NULL.  Replaces a loop of Diagonalize() calls
+ * (jacobi_pd.hpp:159-220) over `batch` matrices of size n x n. */
+JPD_API int jpd_diagonalize_batched_f64(const double* d_mat, double* d_evals, double* d_evecs,
+                                int* d_n_iters, int n, long long batch, int layout,
+                                int sort_criteria, int calc_evecs, int max_num_sweeps,
+                                void* cuda_stream);
+JPD_API int jpd_diagonalize_batched_f32(const float* d_mat, float* d_evals, float* d_evecs,
+                                int* d_n_iters, int n, long long batch, int layout,
+                                int sort_criteria, int calc_evecs, int max_num_sweeps,
+                                void* cuda_stream);
+
+/* ---- host-resident batches ---------------------------------------------------------
+ * Same contract with HOST pointers (pinned memory overlaps best, pageable works).  The
+ * batch is streamed through device `device` in chunks: H2D copy, kernel and D2H copy of
+ * consecutive chunks overlap on three streams.  Synchronous: results are in the host
+ * buffers on return.  This is what the drop-in C++ class Jacobi<>::Diagonalize
+ * (include/jacobi_pd_cuda.hpp) calls with batch == 1. */
+JPD_API int jpd_diagonalize_batched_host_f64(const double* h_mat, double* h_evals, double* h_evecs,
+                                     int* h_n_iters, int n, long long batch, int layout,
+                                     int sort_criteria, int calc_evecs, int max_num_sweeps,
+                                     int device);
+JPD_API int jpd_diagonalize_batched_host_f32(const float* h_mat, float* h_evals, float* h_evecs,
+                                     int* h_n_iters, int n, long long batch, int layout,
+                                     int sort_criteria, int calc_evecs, int max_num_sweeps,
+                                     int device);
+
+/* ---- host-resident batches over several GPUs of one box ----------------------------
+ * Slices [0,batch) into n_devices contiguous parts (part g = [g*ceil(batch/G), ...)) and
+ * runs each part on devices[g] (NULL => 0..n_devices-1) from its own host thread.  The
+ * matrices are independent, so there is no inter-GPU traffic and no collective. */
+JPD_API int jpd_diagonalize_batched_host_multi_f64(const double* h_mat, double* h_evals,
+                                           double* h_evecs, int* h_n_iters, int n,
+                                           long long batch, int layout, int sort_criteria,
+                                           int calc_evecs, int max_num_sweeps,
+                                           int n_devices, const int* devices);
+JPD_API int jpd_diagonalize_batched_host_multi_f32(const float* h_mat, float* h_evals, float* h_evecs,
+                                           int* h_n_iters, int n, long long batch, int layout,
+                                           int sort_criteria, int calc_evecs,
+                                           int max_num_sweeps, int n_devices,
+                                           const int* devices);
+
+/* slice g of G of a batch: first index and length (the partition used above) */
+JPD_API void jpd_slice(long long batch, int n_parts, int part, long long* first, long long* count);
+
+/* ---- synthetic inputs (bench / tests; host twin: oracle/jpd_oracle.c) ---------------
+ * Counter-based generator, identical bits on host and device:
+ *   kind 0: upper-triangle entries iid U(-1,1), mirrored
+ *   kind 1: n == 4, quaternion-superposition overlap matrix of a 3x3 U(-1,1) correlation
+ * Writes matrices b0 .. b0+batch-1 of the stream at local indices 0..batch-1 (device ptr). */
+JPD_API int jpd_fill_synthetic_f64(double* d_mat, int n, long long batch, int layout, int kind,
+                           unsigned long long seed, long long b0, void* cuda_stream);
+JPD_API int jpd_fill_synthetic_f32(float* d_mat, int n, long long batch, int layout, int kind,
+                           unsigned long long seed, long long b0, void* cuda_stream);
+
+/* ---- bookkeeping -------------------------------------------------------------------- */
+/* algorithmic bytes per matrix: elem*(n(n+1)/2 + n + (calc_evecs? n*n : 0)) + 4   */
+JPD_API long long jpd_algorithmic_bytes(int n, int elem_size, int calc_evecs);
+/* which kernel tier the dispatcher picks: 1 thread/matrix, 2 block/matrix in shared
+ * memory, 3 block/matrix with a global (L2) workspace; negative on error */
+JPD_API int jpd_kernel_tier(int n, int elem_size, int calc_evecs);
+/* number of kernels launched by this library in this process so far */
+JPD_API long long jpd_launch_count(void);
+/* free cached device workspaces / staging buffers of all devices */
+JPD_API int jpd_release(void);
+JPD_API const char* jpd_error_string(int code);
+/* text of the last CUDA error seen by this thread's calls ("" if none) */
+JPD_API const char* jpd_last_cuda_error(void);
+JPD_API int jpd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JPD_H_ */

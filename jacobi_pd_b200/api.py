@@ -1,0 +1,168 @@
+"""Host-side mirror of the reference interface for the Diagonalize path.
+
+Reference: ``jacobi_pd::Jacobi<Scalar,Vector,Matrix,ConstMatrix>`` in
+/root/reference/include/jacobi_pd.hpp:25-146 (``Diagonalize`` :76-81, ``SortCriteria``
+:56-62, ``SetSize`` :42).  The real drop-in for C++ callers is
+``include/jacobi_pd_cuda.hpp``; this module is the same surface for Python callers,
+tests and ``bench.py`` -- thin marshalling over the C ABI, PyTorch only as the owner of
+device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+# values as the reference enum (jacobi_pd.hpp:56-62)
+DO_NOT_SORT = 0
+SORT_DECREASING_EVALS = 1
+SORT_INCREASING_EVALS = 2
+SORT_DECREASING_ABS_EVALS = 3
+SORT_INCREASING_ABS_EVALS = 4
+
+LAYOUT_AOS = 0
+LAYOUT_SOA = 1
+
+
+def _suffix(dtype) -> str:
+    import torch
+    if dtype in (torch.float64, np.float64, np.dtype("float64")):
+        return "f64"
+    if dtype in (torch.float32, np.float32, np.dtype("float32")):
+        return "f32"
+    raise TypeError(f"unsupported dtype {dtype}: the path computes in fp64 or fp32")
+
+
+def out_shapes(n: int, batch: int, layout: int):
+    if layout == LAYOUT_AOS:
+        return (batch, n), (batch, n, n)
+    return (n, batch), (n, n, batch)
+
+
+def diagonalize_batched(mat, n: int | None = None, layout: int = LAYOUT_AOS,
+                        sort_criteria: int = SORT_DECREASING_EVALS, calc_evecs: bool = True,
+                        max_num_sweeps: int = 50, out=None, stream=None):
+    """Diagonalise a device-resident batch (torch CUDA tensor) through the C ABI.
+
+    mat: AoS ``(batch, n, n)`` or SoA-interleaved ``(n, n, batch)`` contiguous CUDA tensor.
+    Returns ``(evals, evecs, n_iters)`` device tensors (evecs is None when not requested);
+    eigenvector k is row k (``evecs[b, k, :]`` / ``evecs[k, :, b]``).  Asynchronous on the
+    current torch stream.
+    """
+    import torch
+    if not mat.is_cuda:
+        raise _lib.JpdError("diagonalize_batched needs a CUDA tensor (no CPU fallback); "
+                            "use diagonalize_batched_host for host memory")
+    if not mat.is_contiguous():
+        raise ValueError("mat must be contiguous")
+    if layout == LAYOUT_AOS:
+        batch, n_, n2 = mat.shape
+    else:
+        n_, n2, batch = mat.shape
+    if n_ != n2 or (n is not None and n != n_):
+        raise ValueError("mat must hold square n x n matrices")
+    n = n_
+    sfx = _suffix(mat.dtype)
+    es, vs = out_shapes(n, batch, layout)
+    if out is None:
+        evals = torch.empty(es, dtype=mat.dtype, device=mat.device)
+        evecs = torch.empty(vs, dtype=mat.dtype, device=mat.device) if calc_evecs else None
+        iters = torch.empty((batch,), dtype=torch.int32, device=mat.device)
+    else:
+        evals, evecs, iters = out
+    st = torch.cuda.current_stream(mat.device).cuda_stream if stream is None else stream
+    with torch.cuda.device(mat.device):
+        fn = getattr(_lib.lib(), f"jpd_diagonalize_batched_{sfx}")
+        rc = fn(mat.data_ptr(), evals.data_ptr(), evecs.data_ptr() if evecs is not None else None,
+                iters.data_ptr() if iters is not None else None, n, batch, layout, sort_criteria,
+                1 if calc_evecs else 0, max_num_sweeps, st)
+    _lib.check(rc, f"jpd_diagonalize_batched_{sfx}")
+    return evals, evecs, iters
+
+
+def _host_ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()  # torch CPU tensor (possibly pinned)
+
+
+def diagonalize_batched_host(mat, evals, evecs, n_iters, n: int, batch: int, layout: int = LAYOUT_AOS,
+                             sort_criteria: int = SORT_DECREASING_EVALS, calc_evecs: bool = True,
+                             max_num_sweeps: int = 50, device: int = 0, n_devices: int = 1):
+    """Host buffers in, host buffers out (numpy arrays or CPU torch tensors, written in place)."""
+    dt = mat.dtype
+    sfx = _suffix(dt)
+    l = _lib.lib()
+    if n_devices > 1:
+        fn = getattr(l, f"jpd_diagonalize_batched_host_multi_{sfx}")
+        rc = fn(_host_ptr(mat), _host_ptr(evals), _host_ptr(evecs), _host_ptr(n_iters), n, batch, layout,
+                sort_criteria, 1 if calc_evecs else 0, max_num_sweeps, n_devices, None)
+    else:
+        fn = getattr(l, f"jpd_diagonalize_batched_host_{sfx}")
+        rc = fn(_host_ptr(mat), _host_ptr(evals), _host_ptr(evecs), _host_ptr(n_iters), n, batch, layout,
+                sort_criteria, 1 if calc_evecs else 0, max_num_sweeps, device)
+    _lib.check(rc, fn.__name__ if hasattr(fn, "__name__") else "jpd host call")
+
+
+def fill_synthetic(mat, n: int, batch: int, layout: int, kind: int, seed: int, b0: int = 0):
+    """Fill a CUDA tensor with the counter-based synthetic batch."""
+    import torch
+    sfx = _suffix(mat.dtype)
+    st = torch.cuda.current_stream(mat.device).cuda_stream
+    with torch.cuda.device(mat.device):
+        rc = getattr(_lib.lib(), f"jpd_fill_synthetic_{sfx}")(mat.data_ptr(), n, batch, layout, kind, seed, b0, st)
+    _lib.check(rc, "jpd_fill_synthetic")
+    return mat
+
+
+def slice_of(batch: int, n_parts: int, part: int):
+    """(first, count) of part `part` of `n_parts` -- the multi-GPU partition."""
+    first, count = ctypes.c_longlong(), ctypes.c_longlong()
+    _lib.lib().jpd_slice(batch, n_parts, part, ctypes.byref(first), ctypes.byref(count))
+    return first.value, count.value
+
+
+def algorithmic_bytes(n: int, elem_size: int, calc_evecs: bool = True) -> int:
+    return _lib.lib().jpd_algorithmic_bytes(n, elem_size, 1 if calc_evecs else 0)
+
+
+class Jacobi:
+    """Python twin of ``jacobi_pd::Jacobi`` (jacobi_pd.hpp:25-146) for ONE matrix at a time.
+
+    ``Diagonalize(mat, evals, evecs, sort_criteria, calc_evecs, max_num_sweeps)`` fills
+    the caller's ``evals`` (n) and ``evecs`` (n x n, eigenvector k in row k) numpy arrays in
+    place and returns the number of iterations (>0) or 0 on non-convergence, exactly the
+    reference contract (:64-81).  The work is done on the GPU through the host entry
+    point of the C ABI (batch = 1); a CUDA device is required.
+    """
+    DO_NOT_SORT = DO_NOT_SORT
+    SORT_DECREASING_EVALS = SORT_DECREASING_EVALS
+    SORT_INCREASING_EVALS = SORT_INCREASING_EVALS
+    SORT_DECREASING_ABS_EVALS = SORT_DECREASING_ABS_EVALS
+    SORT_INCREASING_ABS_EVALS = SORT_INCREASING_ABS_EVALS
+
+    def __init__(self, n: int = 0, dtype=np.float64, device: int = 0):
+        self.dtype = np.dtype(dtype)
+        self.device = device
+        self.SetSize(n)
+
+    def SetSize(self, n: int) -> None:
+        self.n = int(n)
+
+    def Diagonalize(self, mat, evals, evecs, sort_criteria: int = SORT_DECREASING_EVALS,
+                    calc_evecs: bool = True, max_num_sweeps: int = 50) -> int:
+        n = self.n
+        m = np.ascontiguousarray(np.asarray(mat, dtype=self.dtype).reshape(n, n))
+        ev = np.empty(n, self.dtype)
+        vec = np.empty((n, n), self.dtype) if calc_evecs else None
+        it = np.zeros(1, np.int32)
+        diagonalize_batched_host(m, ev, vec, it, n, 1, LAYOUT_AOS, sort_criteria, calc_evecs,
+                                 max_num_sweeps, self.device)
+        np.asarray(evals)[...] = ev
+        if calc_evecs:
+            np.asarray(evecs)[...] = vec
+        return int(it[0])
