@@ -123,6 +123,13 @@ JPD_API int jpd_fill_synthetic_f64(double* d_mat, int n, long long batch, int la
 JPD_API int jpd_fill_synthetic_f32(float* d_mat, int n, long long batch, int layout, int kind,
                            unsigned long long seed, long long b0, void* cuda_stream);
 
+/* ---- FMA-pipe probe (bench only) -------------------------------------------------------
+ * Launches a register-only stream of independent FMAs (elem_size 8 = DFMA, 4 = FFMA) and
+ * returns how many FMAs it issues (negative on error); bench.py times it with CUDA events
+ * to obtain the measured FP64/FP32 peak used as the FP-bound roofline denominator. */
+JPD_API long long jpd_fma_probe(int elem_size, int blocks, int threads, int iters, void* d_scratch,
+                                void* cuda_stream);
+
 /* ---- bookkeeping -------------------------------------------------------------------- */
 /* algorithmic bytes per matrix: elem*(n(n+1)/2 + n + (calc_evecs? n*n : 0)) + 4   */
 JPD_API long long jpd_algorithmic_bytes(int n, int elem_size, int calc_evecs);

@@ -27,6 +27,7 @@ SIGNATURES = {
     "jpd_slice": (None, [c_ll, c_int, c_int, ctypes.POINTER(c_ll), ctypes.POINTER(c_ll)]),
     "jpd_fill_synthetic_f64": (c_int, [c_vp, c_int, c_ll, c_int, c_int, c_ull, c_ll, c_vp]),
     "jpd_fill_synthetic_f32": (c_int, [c_vp, c_int, c_ll, c_int, c_int, c_ull, c_ll, c_vp]),
+    "jpd_fma_probe": (c_ll, [c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "jpd_algorithmic_bytes": (c_ll, [c_int, c_int, c_int]),
     "jpd_kernel_tier": (c_int, [c_int, c_int, c_int]),
     "jpd_launch_count": (c_ll, []),

@@ -24,7 +24,7 @@ namespace {
 using namespace jpd;
 
 constexpr int kSmallMaxN = 6;      // tier 1 upper bound (registers only)
-constexpr int kSmallThreads = 128;
+constexpr int kSmallThreads = JPD_SMALL_THREADS;
 constexpr int kMaxDevices = 64;
 
 thread_local std::string g_last_cuda_error;
@@ -153,12 +153,16 @@ int diagonalize_device(const T* mat, T* evals, T* evecs, int* iters, int n, long
   if (sweeps < 0) sweeps = 0;
   calc = calc ? 1 : 0;
   switch (n) {
+#ifndef JPD_VARIANT_BUILD
     case 1: return launch_small<1, T>(mat, evals, evecs, iters, batch, layout, sort, calc, sweeps, st);
     case 2: return launch_small<2, T>(mat, evals, evecs, iters, batch, layout, sort, calc, sweeps, st);
+#endif
     case 3: return launch_small<3, T>(mat, evals, evecs, iters, batch, layout, sort, calc, sweeps, st);
     case 4: return launch_small<4, T>(mat, evals, evecs, iters, batch, layout, sort, calc, sweeps, st);
+#ifndef JPD_VARIANT_BUILD
     case 5: return launch_small<5, T>(mat, evals, evecs, iters, batch, layout, sort, calc, sweeps, st);
     case 6: return launch_small<6, T>(mat, evals, evecs, iters, batch, layout, sort, calc, sweeps, st);
+#endif
     default: break;
   }
   static_assert(kSmallMaxN == 6, "switch above lists the tier-1 sizes");
@@ -347,6 +351,21 @@ int fill_synthetic(T* d_mat, int n, long long batch, int layout, int kind, unsig
   return JPD_OK;
 }
 
+// ------------------------------------------------------------------ FMA-pipe probe
+// Dependent-chain-free FMA stream: 8 independent accumulators per thread, `iters` rounds.
+// bench.py times it with CUDA events to get the measured FP64 / FP32 FMA peak that the
+// FP-bound rooflines (n >= 16) are quoted against (MEASURED_PEAKS.json has no FP64 figure).
+template <typename T>
+__global__ void jpd_fma_probe_kernel(T* out, int iters, T a, T b) {
+  T x0 = T(threadIdx.x), x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = jfma(x0, a, b); x1 = jfma(x1, a, b); x2 = jfma(x2, a, b); x3 = jfma(x3, a, b);
+    x4 = jfma(x4, a, b); x5 = jfma(x5, a, b); x6 = jfma(x6, a, b); x7 = jfma(x7, a, b);
+  }
+  const T r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (r == T(-12345.678)) out[0] = r;  // never true; keeps the chain alive
+}
+
 }  // namespace
 
 // =================================================================== extern "C"
@@ -411,6 +430,17 @@ int jpd_fill_synthetic_f64(double* d_mat, int n, long long batch, int layout, in
 int jpd_fill_synthetic_f32(float* d_mat, int n, long long batch, int layout, int kind,
                            unsigned long long seed, long long b0, void* cuda_stream) {
   return fill_synthetic<float>(d_mat, n, batch, layout, kind, seed, b0, (cudaStream_t)cuda_stream);
+}
+
+long long jpd_fma_probe(int elem_size, int blocks, int threads, int iters, void* d_scratch, void* cuda_stream) {
+  if (blocks < 1 || threads < 32 || threads > 1024 || iters < 1 || !d_scratch) return JPD_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (elem_size == 8) jpd_fma_probe_kernel<double><<<blocks, threads, 0, st>>>((double*)d_scratch, iters, 0.999999, 1e-9);
+  else if (elem_size == 4) jpd_fma_probe_kernel<float><<<blocks, threads, 0, st>>>((float*)d_scratch, iters, 0.999999f, 1e-9f);
+  else return JPD_ERR_INVALID_ARG;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (cudaGetLastError() != cudaSuccess) return JPD_ERR_CUDA;
+  return 8LL * iters * blocks * threads;  // FMAs issued
 }
 
 long long jpd_algorithmic_bytes(int n, int elem_size, int calc_evecs) {

@@ -63,7 +63,7 @@ __global__ void jpd_block_kernel(const T* __restrict__ mat, T* __restrict__ eval
   T* Ms; T* Es;
   T* gw = gwork ? gwork + (size_t)blockIdx.x * work_elems : nullptr;
   if (m_in_smem) { Ms = sm; sm += (size_t)n * ldm; } else { Ms = gw; gw += (size_t)n * ldm; }
-  if (e_in_smem) { Es = sm; sm += (size_t)n * n; } else { Es = gw; }
+  if (e_in_smem) { Es = sm; if (calc_evecs) sm += (size_t)n * n; } else { Es = gw; }
   int* ids = reinterpret_cast<int*>(sm);
   int* rot_total = ids + n;
 

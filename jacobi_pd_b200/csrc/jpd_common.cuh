@@ -70,6 +70,21 @@ JPD_HD bool sign_bit(float x) {
   return std::signbit(x);
 #endif
 }
+// x == +-0, decided on the integer pipe (a DSETP would cost an FP64 issue slot)
+JPD_HD bool is_zero(double x) {
+#if defined(__CUDA_ARCH__)
+  return (((unsigned)__double2hiint(x) << 1) | (unsigned)__double2loint(x)) == 0u;
+#else
+  return x == 0.0;
+#endif
+}
+JPD_HD bool is_zero(float x) {
+#if defined(__CUDA_ARCH__)
+  return ((unsigned)__float_as_int(x) << 1) == 0u;
+#else
+  return x == 0.0f;
+#endif
+}
 // 2^(field - bias) built on the integer pipe; field must be in [1, kExpMask-1].
 JPD_HD double pow2_from_field(int field, double) {
 #if defined(__CUDA_ARCH__)
@@ -146,7 +161,7 @@ JPD_HD bool pair_needs_rotation(T a, T mii, T mjj) {
   const int ea = expo_field(a), ei = expo_field(mii), ej = expo_field(mjj);
   const int emin = ei < ej ? ei : ej;
   const bool negligible = (ea + Fp<T>::kMantBits + 2 <= emin);
-  return (a != T(0)) && !negligible;
+  return !is_zero(a) && !negligible;
 }
 
 // Rotation (c, s, t) = (cos, sin, tan) of the angle that zeroes the (i,j) entry.
@@ -203,7 +218,7 @@ JPD_HD void rescale_for_rotation(T& d, T& a) {
 // nothing when no lane needs it.
 template <typename T>
 JPD_HD void jacobi_rotation(T d, T a, bool any_unsafe, T& c, T& s, T& t) {
-  const bool d_is_zero = (d == T(0));
+  const bool d_is_zero = is_zero(d);
   const bool d_neg = sign_bit(d);
   if (any_unsafe) rescale_for_rotation(d, a);
   rotation_from_scaled(d, a, d_is_zero, d_neg, c, s, t);

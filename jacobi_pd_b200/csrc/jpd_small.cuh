@@ -6,14 +6,23 @@
 //  ApplyRotLeft :409-419, SortRows :477-508).
 //
 // Design ("tier 1"):
-//  * The reference's max-pivot search makes (i,j) data dependent; indexing a register
-//    file dynamically is impossible and branching per pivot would serialise a warp 3x-6x.
+//  * The reference's max-pivot search makes (i,j) data dependent; a register file cannot
+//    be indexed dynamically and branching per pivot would serialise a warp 3x-6x.
 //    Instead every lane walks the SAME static round-robin (chess-tournament) pair order,
 //    fully unrolled, and each lane applies the reference's own skip test to its pair.
 //    Measured rotation counts are within 4% of the max-pivot rule for n=3,4.
-//  * Lanes that do not need a rotation get the identity (c=1,s=0,t=0) via selects, so
-//    the FP64 stream is branch-free; a pair is skipped only when NO lane of the warp
-//    needs it (__any_sync), and the sweep loop exits on a warp vote.
+//  * A sweep is ONE branch-free basic block: lanes whose pair needs no rotation get the
+//    exact identity (c=1,s=0,t=0) through selects.  That lets ptxas interleave the
+//    independent rotations of a round-robin step (FP64 latency hiding) and removes the
+//    per-pair votes / register shuffles that branchy code needs (r1a profile: 64% of the
+//    issued instructions were not FP64).
+//  * Control flow is per sweep and warp-uniform: before a sweep every lane evaluates the
+//    skip test on all its pairs; the warp leaves when no lane has work (__any_sync).
+//  * Range safety without per-pair cost: the common sweep computes x = d^2+(2a)^2
+//    directly; a warp votes once per sweep whether any lane holds entries so large/small
+//    that x could overflow/underflow and only then runs the sweep variant that rescales
+//    (d,a) by a power of two per pair.  A last-resort guard skips (for this sweep only) a
+//    pair whose x still underflowed.
 //  * Upper triangle only (as the reference reads only mat[i][j], j>=i, :167-171);
 //    eigenvectors are rows (:69).
 //  * Sort = the reference's selection sort replayed on (key,id) pairs with static
@@ -41,29 +50,92 @@ template <int N> struct SmallShape {
 #define JPD_WARP_ANY(pred) (pred)
 #endif
 
-// One Jacobi rotation of the static pair (I,J), I<J, on the register-resident matrix.
-template <int N, typename T, bool EVECS, int I, int J>
+// exponent window in which the un-rescaled rotation is safe for every pair of a sweep
+template <typename T> struct SmallRange {
+  static constexpr int kLo = Fp<T>::kBias - (Fp<T>::kSafe * 5) / 6;   // entries >= 2^-400 (fp64)
+  static constexpr int kHi = Fp<T>::kBias + Fp<T>::kSafe;             // entries <  2^481
+  static constexpr int kXMin = Fp<T>::kBias - 2 * Fp<T>::kSafe + Fp<T>::kSafe / 8;  // x >= 2^-900
+  static constexpr int kXMax = Fp<T>::kBias + 2 * Fp<T>::kSafe + Fp<T>::kSafe / 8;  // x <  2^1020
+};
+
+// |x| as an ordered integer: the high word of a double (the whole word of a float) with
+// the sign bit cleared grows monotonically with |x|, so magnitudes can be compared and
+// scaled by powers of two on the integer pipe.
+JPD_HD int abs_key(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2hiint(x) & 0x7fffffff;
+#else
+  std::uint64_t u; std::memcpy(&u, &x, 8);
+  return (int)((u >> 32) & 0x7fffffffu);
+#endif
+}
+JPD_HD int abs_key(float x) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(x) & 0x7fffffff;
+#else
+  std::uint32_t u; std::memcpy(&u, &x, 4);
+  return (int)(u & 0x7fffffffu);
+#endif
+}
+template <typename T> struct KeyShift;   // bit position of the exponent field inside abs_key
+template <> struct KeyShift<double> { static constexpr int value = 20; };
+template <> struct KeyShift<float>  { static constexpr int value = 23; };
+
+// Skip test of the reference (jacobi_pd.hpp:191: a is below half an ulp of BOTH diagonal
+// entries) evaluated as  |a| * 2^(kMant+2) <= min(|mii|,|mjj|)  on abs_key()s.  The bound is
+// inside the reference's skip region, so a pair the reference would rotate is never skipped.
+template <typename T>
+JPD_HD bool key_needs_rotation(int ka, bool a_is_zero, int kii, int kjj) {
+  const int kmin = kii < kjj ? kii : kjj;
+  const int lifted = ka + ((Fp<T>::kMantBits + 2) << KeyShift<T>::value);
+  return !a_is_zero & (lifted > kmin);
+}
+
+// One Jacobi rotation of the static pair (I,J), I<J, branch-free.  The skip test is taken
+// on the CURRENT entries (re-using the sweep-start flags instead was measured: stale flags
+// cost ~4% more rotations and a longer warp-max sweep count).
+template <int N, typename T, bool EVECS, bool SCALED, int I, int J>
 JPD_HD void small_rotate_pair(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N : 1],
-                              bool& rotated, int& n_rot) {
+                              int& n_rot, bool& guard_hit) {
   using Sh = SmallShape<N>;
   const T a = m[Sh::tri(I, J)];
   const T mii = m[Sh::tri(I, I)];
   const T mjj = m[Sh::tri(J, J)];
-  const bool need = pair_needs_rotation(a, mii, mjj);
-  if (!JPD_WARP_ANY(need)) return;
-  const T d = mjj - mii;
-  const bool any_unsafe = JPD_WARP_ANY(need && rotation_range_unsafe(d, a));
-  T c, s, t;
-  jacobi_rotation(d, a, any_unsafe, c, s, t);
+  const bool flagged = key_needs_rotation<T>(abs_key(a), is_zero(a), abs_key(mii), abs_key(mjj));
+  T d = mjj - mii;
+  T as = a;
+  // sign(t) = sign(a) sign(d); the reference takes t = +1 when d == 0 whatever the sign of
+  // a (jacobi_pd.hpp:237-239) -- kept, so that n == 2 agrees with it even unsorted.
+  const bool flip = is_zero(d) ? sign_bit(a) : sign_bit(d);
+  if (SCALED) rescale_for_rotation(d, as);
+  // ---- rotation_from_scaled() of jpd_common.cuh, inlined so the guard can look at x
+  const T a2 = as + as;
+  const T x = jfma(a2, a2, d * d);
+  // x == 0 (pair already exactly diagonal), or x under/overflowed in the un-rescaled
+  // variant: leave the pair alone in this sweep; small_solve() then switches the warp to
+  // the rescaling variant, which has no such limit.
+  const int kx = abs_key(x);
+  const bool x_ok = SCALED ? (kx != 0)
+                           : ((unsigned)(kx - (SmallRange<T>::kXMin << KeyShift<T>::value)) <
+                              (unsigned)((SmallRange<T>::kXMax - SmallRange<T>::kXMin) << KeyShift<T>::value));
+  const bool need = flagged & x_ok;
+  guard_hit = guard_hit | (flagged & !x_ok);
+  const T p = rsqrt_refined(x);
+  const T rho = jabs(d) * p;
+  T ap = as * p;                                   // sin(2 theta) / 2, sign of a
+  ap = flip ? -ap : ap;
+  const T v = jfma(T(0.5), rho, T(0.5));           // cos^2(theta)
+  const T u = rsqrt_refined(v);
+  T c = v * u;
+  T s = ap * u;
+  T t = s * u;
   c = need ? c : T(1);
   s = need ? s : T(0);
   t = need ? t : T(0);
-  rotated = rotated || need;
   n_rot += need ? 1 : 0;
   // diagonal through t, pivot zeroed: jacobi_pd.hpp:337-338,347
-  const T g = t * a;
-  m[Sh::tri(I, I)] = mii - g;
-  m[Sh::tri(J, J)] = mjj + g;
+  m[Sh::tri(I, I)] = jfma(-t, a, mii);
+  m[Sh::tri(J, J)] = jfma(t, a, mjj);
   m[Sh::tri(I, J)] = need ? T(0) : a;
   // the two changed rows/columns, upper-triangle names: jacobi_pd.hpp:350-390
 #pragma unroll
@@ -71,38 +143,58 @@ JPD_HD void small_rotate_pair(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N 
     if (k == I || k == J) continue;
     const int ki = k < I ? Sh::tri(k, I) : Sh::tri(I, k);
     const int kj = k < J ? Sh::tri(k, J) : Sh::tri(J, k);
-    const T x = m[ki], y = m[kj];
-    m[ki] = c * x - s * y;
-    m[kj] = s * x + c * y;
+    const T xx = m[ki], yy = m[kj];
+    m[ki] = jfma(c, xx, -(s * yy));
+    m[kj] = jfma(s, xx, c * yy);
   }
   // eigenvector rows I and J: jacobi_pd.hpp:414-418
   if (EVECS) {
 #pragma unroll
-    for (int v = 0; v < N; ++v) {
-      const T x = e[I * N + v], y = e[J * N + v];
-      e[I * N + v] = c * x - s * y;
-      e[J * N + v] = s * x + c * y;
+    for (int w = 0; w < N; ++w) {
+      const T xx = e[I * N + w], yy = e[J * N + w];
+      e[I * N + w] = jfma(c, xx, -(s * yy));
+      e[J * N + w] = jfma(s, xx, c * yy);
     }
   }
 }
 
 // One full round-robin sweep, unrolled at compile time: pair P of kSteps*kHalf.
-template <int N, typename T, bool EVECS, int P>
+template <int N, typename T, bool EVECS, bool SCALED, int P>
 JPD_HD void small_sweep_from(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N : 1],
-                             bool& rotated, int& n_rot) {
+                             int& n_rot, bool& guard_hit) {
   using Sh = SmallShape<N>;
   if constexpr (P < Sh::kSteps * Sh::kHalf) {
     constexpr int S = P / Sh::kHalf, K = P % Sh::kHalf;
     constexpr int A = Sh::player_a(S, K), B = Sh::player_b(S, K);
     if constexpr (A < N && B < N)  // a pair with the dummy player (odd N) sits out
-      small_rotate_pair<N, T, EVECS, (A < B ? A : B), (A < B ? B : A)>(m, e, rotated, n_rot);
-    small_sweep_from<N, T, EVECS, P + 1>(m, e, rotated, n_rot);
+      small_rotate_pair<N, T, EVECS, SCALED, (A < B ? A : B), (A < B ? B : A)>(m, e, n_rot, guard_hit);
+    small_sweep_from<N, T, EVECS, SCALED, P + 1>(m, e, n_rot, guard_hit);
   }
 }
 
+// Sweep-start status of one lane: the skip test of every pair (in schedule order).
+template <int N, typename T>
+JPD_HD bool small_status(const T (&m)[SmallShape<N>::kTri]) {
+  using Sh = SmallShape<N>;
+  int key[Sh::kTri];
+#pragma unroll
+  for (int k = 0; k < Sh::kTri; ++k) key[k] = abs_key(m[k]);
+  bool any_need = false;
+#pragma unroll
+  for (int P = 0; P < Sh::kSteps * Sh::kHalf; ++P) {
+    const int A = Sh::player_a(P / Sh::kHalf, P % Sh::kHalf), B = Sh::player_b(P / Sh::kHalf, P % Sh::kHalf);
+    if (A < N && B < N) {
+      const int i = A < B ? A : B, j = A < B ? B : A;
+      any_need = any_need | key_needs_rotation<T>(key[Sh::tri(i, j)], is_zero(m[Sh::tri(i, j)]),
+                                                  key[Sh::tri(i, i)], key[Sh::tri(j, j)]);
+    }
+  }
+  return any_need;
+}
+
 // Diagonalise the register-resident matrix. Returns the reference's return value:
-// rotations + 1 (> 0) once a whole sweep found nothing to rotate, 0 if max_num_sweeps
-// sweeps did not get there and n > 1 (jacobi_pd.hpp:214-219).
+// rotations + 1 (> 0) once a sweep starts with nothing left to rotate, 0 if that was not
+// observed within max_num_sweeps sweeps and n > 1 (jacobi_pd.hpp:214-219).
 template <int N, typename T, bool EVECS>
 JPD_HD int small_solve(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N : 1], int max_num_sweeps) {
   if (EVECS) {
@@ -114,11 +206,15 @@ JPD_HD int small_solve(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N : 1], i
   if (N == 1) return 1;
   int n_rot = 0;
   bool converged = false;
+  bool rescale = false;  // warp-uniform: a lane met an x outside the safe window
   for (int sweep = 0; sweep < max_num_sweeps; ++sweep) {
-    bool rotated = false;
-    small_sweep_from<N, T, EVECS, 0>(m, e, rotated, n_rot);
-    converged = converged || !rotated;
-    if (!JPD_WARP_ANY(!converged)) break;
+    const bool any_need = small_status<N, T>(m);
+    converged = converged || !any_need;
+    if (!JPD_WARP_ANY(any_need)) break;
+    bool guard_hit = false;
+    if (rescale) small_sweep_from<N, T, EVECS, true, 0>(m, e, n_rot, guard_hit);
+    else         small_sweep_from<N, T, EVECS, false, 0>(m, e, n_rot, guard_hit);
+    rescale = rescale || JPD_WARP_ANY(guard_hit);
   }
   return converged ? n_rot + 1 : 0;
 }
@@ -164,9 +260,24 @@ JPD_HD void small_sort_ids(const T (&ev)[N], int sort_criteria, int (&id)[N]) {
 
 #if defined(__CUDACC__)
 
+#ifndef JPD_SMALL_THREADS
+#define JPD_SMALL_THREADS 128
+#endif
+#ifndef JPD_MINB_N3
+#define JPD_MINB_N3 8
+#endif
+#ifndef JPD_MINB_N4
+#define JPD_MINB_N4 6
+#endif
+template <int N, typename T> struct SmallLaunch {
+  // resident blocks per SM the register allocator is asked to make room for
+  static constexpr int kMinBlocks = (sizeof(T) == 8) ? (N <= 2 ? 8 : (N == 3 ? JPD_MINB_N3 : (N == 4 ? JPD_MINB_N4 : (N == 5 ? 4 : 2))))
+                                                     : (N <= 4 ? 8 : (N == 5 ? 6 : 4));
+};
+
 // layout 0 (AoS): mat[b*N*N + i*N + j]; layout 1 (SoA-interleaved): mat[(i*N+j)*batch + b]
 template <int N, typename T, bool SOA, bool EVECS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(JPD_SMALL_THREADS, SmallLaunch<N, T>::kMinBlocks)
 jpd_small_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict__ evecs,
                  int* __restrict__ n_iters, long long batch, int sort_criteria,
                  int max_num_sweeps) {

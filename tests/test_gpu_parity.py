@@ -1,0 +1,85 @@
+"""-m gpu: CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances are the north star's: eigenvalues within 1e-12*max|l| (fp64) / 1e-5 (fp32) at
+the same sorted position, eigenvectors equal up to sign where the spectrum is separated,
+residual and orthogonality within tol*n, same convergence flag.  See tests/parity.py.
+"""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+import parity
+from gpu_util import run_gpu
+
+pytestmark = pytest.mark.gpu
+
+SIZES_SMALL = [1, 2, 3, 4, 5, 6]
+SIZES_BLOCK = [7, 8, 9, 12, 16, 17, 20, 31, 32, 33, 50, 64]
+
+
+def _batch_for(n):
+    return 4096 if n <= 6 else (256 if n <= 20 else (64 if n <= 64 else 8))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", SIZES_SMALL + SIZES_BLOCK)
+def test_parity_uniform(n, dtype):
+    A = ob.fill_synthetic(n, _batch_for(n), seed=1234 + n, dtype=dtype)
+    ref = ob.oracle_diagonalize(A, 1)
+    for layout in (0, 1):
+        out = run_gpu(A, 1, layout=layout)
+        parity.full_check(A, out, ref, 1)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 8, 20, 33])
+@pytest.mark.parametrize("sort", [0, 1, 2, 3, 4])
+def test_all_sort_criteria(n, sort):
+    A = ob.fill_synthetic(n, 512 if n <= 6 else 64, seed=77 + n)
+    ref = ob.oracle_diagonalize(A, sort)
+    out = run_gpu(A, sort)
+    parity.full_check(A, out, ref, sort)
+
+
+@pytest.mark.parametrize("n", [3, 4, 6, 16, 40])
+def test_no_evecs_and_sweep_limits(n):
+    A = ob.fill_synthetic(n, 300, seed=5 + n)
+    ref = ob.oracle_diagonalize(A, 1)
+    ev, vec, it = run_gpu(A, 1, calc=False)
+    assert vec is None
+    parity.check_evals(ev, ref[0])
+    parity.check_iters(it, ref[2])
+    # max_num_sweeps = 0: reference returns 0, evals = sorted diagonal, evecs = permuted identity
+    ref0 = ob.oracle_diagonalize(A, 1, True, 0)
+    ev0, vec0, it0 = run_gpu(A, 1, sweeps=0)
+    assert (it0 == 0).all() and (ref0[2] == 0).all()
+    assert np.array_equal(ev0, ref0[0]) and np.array_equal(vec0, ref0[1])
+
+
+@pytest.mark.parametrize("n", [128, 256])
+def test_parity_large(n):
+    A = ob.fill_synthetic(n, 4 if n == 128 else 2, seed=9000 + n)
+    ref = ob.oracle_diagonalize(A, 1)
+    out = run_gpu(A, 1)
+    parity.full_check(A, out, ref, 1)
+
+
+def test_host_api_matches_device_api():
+    for n, layout in ((4, 0), (4, 1), (3, 0), (12, 0), (12, 1)):
+        A = ob.fill_synthetic(n, 1000, seed=31 + n)
+        a = run_gpu(A, 1, layout=layout)
+        b = run_gpu(A, 1, layout=layout, host_api=True)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+
+
+def test_synthetic_generator_bits_match_host_twin():
+    import torch
+    import jacobi_pd_b200 as jpd
+    for n, kind, layout in ((3, 0, 0), (3, 0, 1), (4, 1, 0), (4, 1, 1), (32, 0, 0)):
+        B = 777
+        shape = (B, n, n) if layout == 0 else (n, n, B)
+        for dt, tdt in ((np.float64, torch.float64), (np.float32, torch.float32)):
+            d = torch.empty(shape, dtype=tdt, device="cuda")
+            jpd.fill_synthetic(d, n, B, layout, kind, 4321, b0=5)
+            h = ob.fill_synthetic(n, B, layout, kind, 4321, b0=5, dtype=dt)
+            assert np.array_equal(d.cpu().numpy(), h)
