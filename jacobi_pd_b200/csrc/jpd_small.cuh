@@ -87,8 +87,9 @@ template <> struct KeyShift<float>  { static constexpr int value = 23; };
 template <typename T>
 JPD_HD bool key_needs_rotation(int ka, bool a_is_zero, int kii, int kjj) {
   const int kmin = kii < kjj ? kii : kjj;
-  const int lifted = ka + ((Fp<T>::kMantBits + 2) << KeyShift<T>::value);
-  return !a_is_zero & (lifted > kmin);
+  // (kmin - shift rather than ka + shift: the latter overflows int for |a| > 2^970)
+  const int lowered = kmin - ((Fp<T>::kMantBits + 2) << KeyShift<T>::value);
+  return !a_is_zero & (ka > lowered);
 }
 
 // One Jacobi rotation of the static pair (I,J), I<J, branch-free.  The skip test is taken

@@ -1,0 +1,85 @@
+"""CPU-only checks of the drop-in boundary: libjpd.so loads, exports every symbol that
+include/jpd.h declares, rejects bad arguments before touching the GPU, and the pure host
+helpers (slicing, byte model, tier choice) behave.  No compute call is made here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import jacobi_pd_b200 as jpd
+from jacobi_pd_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    with open(os.path.join(ROOT, "include", "jpd.h")) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"JPD_API\s+[\w\s\*]+?\b(jpd_\w+)\s*\(", text)))
+
+
+def test_library_is_built_in_tree():
+    assert os.path.exists(jpd.LIB_PATH) and jpd.LIB_PATH.startswith(ROOT)
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    syms = declared_symbols()
+    assert len(syms) >= 15 and "jpd_diagonalize_batched_f64" in syms and "jpd_diagonalize_batched_f32" in syms
+    handle = ctypes.CDLL(jpd.LIB_PATH)
+    for s in syms:
+        assert getattr(handle, s) is not None
+    assert sorted(_lib.SIGNATURES) == syms      # the Python binding covers exactly the header
+
+
+def test_header_cites_the_reference_interface():
+    with open(os.path.join(ROOT, "include", "jpd.h")) as f:
+        text = f.read()
+    assert "jacobi_pd.hpp:76-81" in text and "jacobi_pd.hpp:159-220" in text
+
+
+def test_argument_validation_needs_no_gpu():
+    l = jpd.lib()
+    f = l.jpd_diagonalize_batched_f64
+    assert f(None, None, None, None, 0, 10, 0, 1, 1, 50, None) == -1          # n < 1
+    assert f(None, None, None, None, 4, -1, 0, 1, 1, 50, None) == -1          # negative batch
+    assert f(None, None, None, None, 4, 10, 7, 1, 1, 50, None) == -1          # unknown layout
+    assert f(None, None, None, None, 4, 10, 0, 1, 1, 50, None) == -1          # null pointers
+    assert f(None, None, None, None, 5000, 10, 0, 1, 1, 50, None) == -1       # n > JPD_MAX_N
+    assert f(None, None, None, None, 4, 0, 0, 1, 1, 50, None) == 0            # empty batch is a no-op
+    assert l.jpd_diagonalize_batched_host_f64(None, None, None, None, 4, 0, 0, 1, 1, 50, 0) == 0
+    assert l.jpd_diagonalize_batched_host_f32(None, None, None, None, 4, 5, 0, 1, 1, 50, 0) == -1
+    assert l.jpd_fill_synthetic_f64(None, 4, 5, 0, 0, 1, 0, None) == -1
+    assert l.jpd_error_string(-1).decode() == "invalid argument"
+    assert l.jpd_version() >= 100
+
+
+def test_slices_partition_the_batch():
+    for batch in (0, 1, 7, 1000, 16777216, 16777217):
+        for parts in (1, 2, 3, 4, 8):
+            got, end = 0, 0
+            for p in range(parts):
+                first, count = jpd.slice_of(batch, parts, p)
+                assert first == end or count == 0
+                end = max(end, first + count)
+                got += count
+            assert got == batch and end == batch
+
+
+def test_byte_model_and_tiers():
+    assert jpd.algorithmic_bytes(3, 8) == 148 and jpd.algorithmic_bytes(4, 8) == 244
+    assert jpd.algorithmic_bytes(32, 8) == 12676 and jpd.algorithmic_bytes(3, 4) == 76
+    assert jpd.algorithmic_bytes(4, 8, False) == 244 - 128
+    l = jpd.lib()
+    assert [l.jpd_kernel_tier(n, 8, 1) for n in (1, 3, 4, 6)] == [1, 1, 1, 1]
+    assert l.jpd_kernel_tier(32, 8, 1) == 2 and l.jpd_kernel_tier(256, 8, 1) == 3
+
+
+def test_no_silent_cpu_fallback():
+    """Without a CUDA tensor the Python front end refuses instead of computing on the host."""
+    import torch
+    with pytest.raises(jpd.JpdError):
+        jpd.diagonalize_batched(torch.zeros(2, 3, 3, dtype=torch.float64))
+    import inspect
+    src = inspect.getsource(jpd.api) + inspect.getsource(_lib)
+    assert "oracle" not in src.replace("never imported", "")     # product never reaches into oracle/
