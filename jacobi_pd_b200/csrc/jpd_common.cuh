@@ -85,6 +85,22 @@ JPD_HD bool is_zero(float x) {
   return x == 0.0f;
 #endif
 }
+// v with its sign flipped iff the sign bit of `src` is set (integer pipe: one LOP3 on the
+// high word instead of an FP64 negate plus two selects)
+JPD_HD double xor_sign(double v, double src) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(v) ^ (__double2hiint(src) & (int)0x80000000), __double2loint(v));
+#else
+  return std::signbit(src) ? -v : v;
+#endif
+}
+JPD_HD float xor_sign(float v, float src) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(__float_as_int(v) ^ (__float_as_int(src) & (int)0x80000000));
+#else
+  return std::signbit(src) ? -v : v;
+#endif
+}
 // 2^(field - bias) built on the integer pipe; field must be in [1, kExpMask-1].
 JPD_HD double pow2_from_field(int field, double) {
 #if defined(__CUDA_ARCH__)
@@ -122,30 +138,49 @@ JPD_HD float jabs(float a) { return fabsf(a); }
 // correction on the FMA pipe.  fp64: cubic step, 5 DFMA-class ops, no division, no
 // IEEE sqrt expansion (the reference's 3 div + 2 sqrt expand to ~100 FP64-pipe
 // instructions on sm_100; see DESIGN.md "rotation").
-JPD_HD double rsqrt_refined(double x) {
+// (split in seed + correction so that callers can put independent work between the two)
+JPD_HD double rsqrt_seed(double x) {
 #if defined(__CUDA_ARCH__)
   double y0;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  return y0;
+#else
+  return 1.0 / std::sqrt(x);
+#endif
+}
+JPD_HD double rsqrt_correct(double x, double y0) {
+#if defined(__CUDA_ARCH__)
   double xy = x * y0;
   double e = __fma_rn(-xy, y0, 1.0);       // 1 - x*y0^2, |e| <~ 2^-21
   double r = __fma_rn(0.375, e, 0.5);      // 1/2 + 3/8 e
   double ey = e * y0;
   return __fma_rn(r, ey, y0);              // y0 (1 + e/2 + 3/8 e^2)
 #else
-  return 1.0 / std::sqrt(x);
+  (void)x;
+  return y0;
 #endif
 }
-JPD_HD float rsqrt_refined(float x) {
+JPD_HD float rsqrt_seed(float x) {
 #if defined(__CUDA_ARCH__)
   float y0;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(x));
-  float xy = x * y0;
-  float e = __fmaf_rn(-xy, y0, 1.0f);
-  return __fmaf_rn(0.5f * y0, e, y0);      // one Newton step
+  return y0;
 #else
   return (float)(1.0 / std::sqrt((double)x));
 #endif
 }
+JPD_HD float rsqrt_correct(float x, float y0) {
+#if defined(__CUDA_ARCH__)
+  float xy = x * y0;
+  float e = __fmaf_rn(-xy, y0, 1.0f);
+  return __fmaf_rn(0.5f * y0, e, y0);      // one Newton step
+#else
+  (void)x;
+  return y0;
+#endif
+}
+JPD_HD double rsqrt_refined(double x) { return rsqrt_correct(x, rsqrt_seed(x)); }
+JPD_HD float rsqrt_refined(float x) { return rsqrt_correct(x, rsqrt_seed(x)); }
 
 // Is the off-diagonal `a` still worth rotating against its two diagonal entries?
 // Reference test (jacobi_pd.hpp:191): skip iff  (mii + a == mii) && (mjj + a == mjj),

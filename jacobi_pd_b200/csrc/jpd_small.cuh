@@ -107,7 +107,7 @@ JPD_HD void small_rotate_pair(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N 
   T as = a;
   // sign(t) = sign(a) sign(d); the reference takes t = +1 when d == 0 whatever the sign of
   // a (jacobi_pd.hpp:237-239) -- kept, so that n == 2 agrees with it even unsorted.
-  const bool flip = is_zero(d) ? sign_bit(a) : sign_bit(d);
+  const T sign_src = is_zero(d) ? a : d;
   if (SCALED) rescale_for_rotation(d, as);
   // ---- rotation_from_scaled() of jpd_common.cuh, inlined so the guard can look at x
   const T a2 = as + as;
@@ -123,8 +123,7 @@ JPD_HD void small_rotate_pair(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N 
   guard_hit = guard_hit | (flagged & !x_ok);
   const T p = rsqrt_refined(x);
   const T rho = jabs(d) * p;
-  T ap = as * p;                                   // sin(2 theta) / 2, sign of a
-  ap = flip ? -ap : ap;
+  const T ap = xor_sign(as * p, sign_src);         // sin(2 theta) / 2 with the sign of t
   const T v = jfma(T(0.5), rho, T(0.5));           // cos^2(theta)
   const T u = rsqrt_refined(v);
   T c = v * u;
@@ -307,28 +306,32 @@ jpd_small_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict
 
   if (!live) return;
   if (n_iters) n_iters[b] = iters;
+  // The sort permutes DESTINATIONS, not data: source row r goes to output row pos[r].  (Moving
+  // the rows through selects or a local-memory table costs ~200 more instructions per matrix;
+  // the scattered 8-byte stores of one warp still fill whole sectors over the N rows and are
+  // merged in L2 -- DRAM traffic stays at the algorithmic 8(N+N^2)+4 bytes, see profiles/.)
+  int pos[N];
 #pragma unroll
-  for (int k = 0; k < N; ++k) {
-    T val = ev[k];
+  for (int r = 0; r < N; ++r) {
+    pos[r] = r;
     if (sorted) {
 #pragma unroll
-      for (int r = 0; r < N; ++r) val = (id[k] == r) ? ev[r] : val;
+      for (int k = 0; k < N; ++k) pos[r] = (id[k] == r) ? k : pos[r];
     }
-    if (SOA) evals[(long long)k * batch + b] = val;
-    else evals[b * N + k] = val;
+  }
+#pragma unroll
+  for (int r = 0; r < N; ++r) {
+    if (SOA) evals[(long long)pos[r] * batch + b] = ev[r];
+    else evals[b * N + pos[r]] = ev[r];
   }
   if (EVECS) {
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
+    for (int r = 0; r < N; ++r) {
+      T* row = SOA ? evecs + (long long)pos[r] * N * batch + b : evecs + b * (N * N) + pos[r] * N;
 #pragma unroll
       for (int v = 0; v < N; ++v) {
-        T val = e[k * N + v];
-        if (sorted) {
-#pragma unroll
-          for (int r = 0; r < N; ++r) val = (id[k] == r) ? e[r * N + v] : val;
-        }
-        if (SOA) evecs[(long long)(k * N + v) * batch + b] = val;
-        else evecs[b * (N * N) + k * N + v] = val;
+        if (SOA) row[(long long)v * batch] = e[r * N + v];
+        else row[v] = e[r * N + v];
       }
     }
   }
