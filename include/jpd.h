@@ -133,8 +133,9 @@ JPD_API long long jpd_fma_probe(int elem_size, int blocks, int threads, int iter
 /* ---- bookkeeping -------------------------------------------------------------------- */
 /* algorithmic bytes per matrix: elem*(n(n+1)/2 + n + (calc_evecs? n*n : 0)) + 4   */
 JPD_API long long jpd_algorithmic_bytes(int n, int elem_size, int calc_evecs);
-/* which kernel tier the dispatcher picks: 1 thread/matrix, 2 block/matrix in shared
- * memory, 3 block/matrix with a global (L2) workspace; negative on error */
+/* which kernel tier the dispatcher picks: 1 thread/matrix (n <= 6), 2 warp/matrix
+ * (n <= 32), 3 block/matrix in shared memory, 4 block/matrix with a global (L2)
+ * workspace; negative on error */
 JPD_API int jpd_kernel_tier(int n, int elem_size, int calc_evecs);
 /* number of kernels launched by this library in this process so far */
 JPD_API long long jpd_launch_count(void);

@@ -18,6 +18,7 @@
 #include "jpd.h"
 #include "jpd_block.cuh"
 #include "jpd_small.cuh"
+#include "jpd_warp.cuh"
 
 namespace {
 
@@ -80,7 +81,30 @@ int launch_small(const T* mat, T* evals, T* evecs, int* iters, long long batch, 
   return JPD_OK;
 }
 
-// ------------------------------------------------------------------ tier 2/3 plan + launch
+// ------------------------------------------------------------------ tier 2 launch (warp per matrix)
+constexpr int kWarpMaxN = 32;
+constexpr int kWarpThreads = JPD_WARP_THREADS;
+
+template <typename T, int NP>
+int launch_warp(const T* mat, T* evals, T* evecs, int* iters, int n, long long batch, int layout,
+                int sort, int calc, int sweeps, cudaStream_t st) {
+  using Sh = WarpShape<NP>;
+  constexpr int warps = kWarpThreads / 32;
+  const long long per_block = (long long)warps * Sh::kGroups;
+  const long long blocks = (batch + per_block - 1) / per_block;
+  if (blocks > 0x7fffffffLL) return JPD_ERR_UNSUPPORTED;
+  const size_t smem = Sh::block_bytes(sizeof(T), warps);
+  auto kernel = calc ? jpd_warp_kernel<T, NP, true> : jpd_warp_kernel<T, NP, false>;
+  if (smem > 48 * 1024)
+    JPD_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kernel<<<dim3((unsigned)blocks), dim3(kWarpThreads), smem, st>>>(
+      mat, evals, evecs, iters, n, batch, layout == JPD_LAYOUT_SOA ? 1 : 0, sort, sweeps);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  JPD_CK(cudaGetLastError());
+  return JPD_OK;
+}
+
+// ------------------------------------------------------------------ tier 3/4 plan + launch
 BlockPlan make_block_plan(int n, int elem, int calc, int smem_limit) {
   BlockPlan p{};
   const int m = n + (n & 1), half = m / 2;
@@ -166,6 +190,9 @@ int diagonalize_device(const T* mat, T* evals, T* evecs, int* iters, int n, long
     default: break;
   }
   static_assert(kSmallMaxN == 6, "switch above lists the tier-1 sizes");
+  if (n <= 8) return launch_warp<T, 8>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
+  if (n <= 16) return launch_warp<T, 16>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
+  if (n <= kWarpMaxN) return launch_warp<T, 32>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
   return launch_block<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
 }
 
@@ -452,6 +479,7 @@ long long jpd_algorithmic_bytes(int n, int elem_size, int calc_evecs) {
 int jpd_kernel_tier(int n, int elem_size, int calc_evecs) {
   if (n < 1 || n > JPD_MAX_N || (elem_size != 4 && elem_size != 8)) return JPD_ERR_INVALID_ARG;
   if (n <= kSmallMaxN) return 1;
+  if (n <= kWarpMaxN) return 2;
   int limit = 232448, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) {
     DeviceInfo info;
@@ -460,7 +488,7 @@ int jpd_kernel_tier(int n, int elem_size, int calc_evecs) {
     (void)cudaGetLastError();
   }
   const BlockPlan p = make_block_plan(n, elem_size, calc_evecs ? 1 : 0, limit);
-  return (p.m_in_smem && p.e_in_smem) ? 2 : 3;
+  return (p.m_in_smem && p.e_in_smem) ? 3 : 4;
 }
 
 long long jpd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -1,6 +1,10 @@
 import sys, time; sys.path.insert(0,'.')
 import torch, jacobi_pd_b200 as jpd
-for n, B, kind, dt in ((4, 1<<24, 1, torch.float64), (3, 1<<23, 0, torch.float64), (4, 1<<24, 0, torch.float32), (16, 1<<16, 0, torch.float64), (32, 1<<15, 0, torch.float64), (64, 4096, 0, torch.float64), (128, 1024, 0, torch.float64), (256, 256, 0, torch.float64)):
+cases = ((4, 1<<24, 1, torch.float64), (3, 1<<23, 0, torch.float64), (8, 1<<18, 0, torch.float64), (16, 1<<18, 0, torch.float64), (16, 1<<18, 0, torch.float32), (32, 1<<17, 0, torch.float64), (32, 1<<17, 0, torch.float32), (64, 4096, 0, torch.float64), (128, 1024, 0, torch.float64), (256, 256, 0, torch.float64))
+if len(sys.argv) > 1:
+    want = set(int(x) for x in sys.argv[1].split(','))
+    cases = [c for c in cases if c[0] in want]
+for n, B, kind, dt in cases:
     for layout in ((1,0) if n<=6 else (0,)):
         shape = (B,n,n) if layout==0 else (n,n,B)
         m = torch.empty(shape, dtype=dt, device='cuda'); jpd.fill_synthetic(m, n, B, layout, kind, 4321)
