@@ -16,15 +16,15 @@
 //  * Because the pairings are static, the eigenvector accumulation lives in REGISTERS:
 //    lane v owns column v of E, its rows are registers with compile-time names, and a
 //    step is NP/2 independent 2x2 row operations per lane (4 FP64 instructions each).
-//  * M lives in shared memory, upper triangle only, with one phantom row/column on either
-//    side (-1 and m): pattern B is then pattern A shifted by one position, its two
-//    unpaired end positions being paired with a phantom through the constant "rotation"
-//    (c,s) = (0,-+1), which reproduces them unchanged.  Columns are stored even/odd split
-//    so that the lanes of a warp (consecutive 2x2 blocks of one block row) always touch
-//    consecutive addresses: no bank conflicts in either pattern.
-//  * A step = phase 1 (one lane per pair: the reference's skip test :191, rotation, the
-//    pair's own three entries, (c,s) to shared memory) + phase 2 (all lanes: each 2x2
-//    block {pair K} x {pair L}, K<L, gets G_K B G_L^T once: 16 FP64 instructions; E rows).
+//  * M lives in shared memory, upper triangle only, columns stored even/odd split.  A step
+//    = phase 1 (one lane per pair: the reference's skip test :191, rotation, the pair's own
+//    three entries, (c,s) to shared memory) + phase 2 (all lanes: each 2x2 block
+//    {pair K} x {pair L}, K<L, gets G_K B G_L^T once: 16 FP64 instructions; in pattern B
+//    also the 1x2 / 2x1 strips of the two unpaired end positions; E rows).
+//  * Shared-memory banks: with a row pitch == 3 (mod 8) elements the bank of a block is
+//    (6K + L) mod 16; the lane that handles a block is chosen as exactly that residue and
+//    blocks of one residue class go to different half-warp slots, so every access of every
+//    half-warp touches 16 different banks (tables built once per thread block).
 //  * Convergence = the reference's test applied to ALL pairs at the start of each sweep
 //    (cheap next to a sweep), so no empty sweep is ever executed.
 //  * Return value as the reference: rotations + 1, or 0 when max_num_sweeps sweeps were
@@ -35,32 +35,27 @@
 namespace jpd {
 
 template <int NP> struct WarpShape {
-  static constexpr int kH = NP / 2 + 1;            // column slots per parity class
-  static constexpr int kLd = 2 * kH;               // NP + 2 elements per stored row
-  static constexpr int kRows = NP + 2;             // positions -1 .. NP
-  static constexpr int kMElems = kRows * kLd;
-  static constexpr int kPairsMax = NP / 2 + 1;
-  static constexpr int kGroups = 32 / NP;          // matrices per warp
-  static constexpr int kBlkMaxA = (NP / 2) * (NP / 2 - 1) / 2;
-  static constexpr int kBlkMaxB = (NP / 2 + 1) * (NP / 2) / 2;
-  static constexpr int kItA = (kBlkMaxA + NP - 1) / NP;
-  static constexpr int kItB = (kBlkMaxB + NP - 1) / NP;
-  // per-group shared memory, in elements of T: M, (c,s) pairs, eigenvalues; then ints
-  static constexpr int kGroupElems = kMElems + 2 * kPairsMax + NP + 2;
+  static constexpr int kH = NP / 2;                               // column slots per parity class
+  static constexpr int kLd = (NP == 8) ? 9 : NP + 3;              // row pitch: 35, 19 (== 3 mod 8), 9
+  static constexpr int kBankMul = (2 * kLd) & 15;                 // bank(block K,L) = kBankMul*K + L
+  static constexpr int kMElems = NP * kLd;
+  static constexpr int kPairsMax = NP / 2;
+  static constexpr int kGroups = 32 / NP;                         // matrices per warp
+  static constexpr int kClasses = NP < 16 ? NP : 16;              // bank residue classes = lanes of a half warp
+  static constexpr int kHalves = NP / kClasses;                   // half warps per matrix
+  static constexpr int kIt = (NP == 32) ? 4 : (NP == 16 ? 2 : 1); // block iterations per step (both patterns)
+  static constexpr int kTblEntries = kIt * NP;
+  // per-group shared memory, in elements of T: M | (c,s) interleaved | c | s | eigenvalues
+  static constexpr int kGroupElems = kMElems + 2 * kPairsMax + kPairsMax + kPairsMax + NP;
   JPD_CX static constexpr size_t group_bytes(size_t elem) {
     return ((kGroupElems * elem + NP * sizeof(int)) + 15) / 16 * 16;
   }
-  JPD_CX static constexpr size_t table_bytes() {
-    return ((size_t)(kBlkMaxA + kBlkMaxB) * sizeof(unsigned) + 15) / 16 * 16;
-  }
+  JPD_CX static constexpr size_t table_bytes() { return (size_t)2 * kTblEntries * sizeof(unsigned); }
   JPD_CX static constexpr size_t block_bytes(size_t elem, int warps) {
     return table_bytes() + (size_t)warps * kGroups * group_bytes(elem);
   }
-  // storage offset of element (r,c), r,c in [-1, NP]
-  JPD_HD static int addr(int r, int c) {
-    const int x = c + 1;
-    return (r + 1) * kLd + (x >> 1) + (x & 1) * kH;
-  }
+  // storage offset of element (r,c), 0 <= r,c < NP
+  JPD_HD static int addr(int r, int c) { return r * kLd + (c >> 1) + (c & 1) * kH; }
 };
 
 #if defined(__CUDACC__)
@@ -79,87 +74,110 @@ __device__ __forceinline__ long long sortable_bits(float x) {
   return (long long)(k ^ ((k >> 31) & 0x7fffffff));
 }
 
-// flat index over {(K,L): 0 <= K < L < np}, row-major in K  ->  (K,L)
-__device__ __forceinline__ void tri_decode(int f, int np, int& K, int& L) {
-  int k = 0, rem = f;
-  while (rem >= np - 1 - k) { rem -= np - 1 - k; ++k; }
-  K = k;
-  L = k + 1 + rem;
+// Schedule table of one pattern: entry [it*NP + lane] = offset of the block's first element
+// | K << 16 | L << 24, or 0xffffffff when the lane idles in that iteration.  `off` is the
+// position of pair 0's first index (0: pattern A, 1: pattern B), `npr` the number of pairs.
+template <int NP>
+__device__ __forceinline__ void build_schedule(unsigned* tbl, int npr, int off) {
+  using Sh = WarpShape<NP>;
+  for (int i = threadIdx.x; i < Sh::kTblEntries; i += blockDim.x) tbl[i] = 0xffffffffu;
+  __syncthreads();
+  if (threadIdx.x < Sh::kClasses) {
+    const int cl = threadIdx.x;
+    int slot = 0;
+    for (int K = 0; K < npr; ++K) {
+      const int L = (cl - Sh::kBankMul * K) & (Sh::kClasses - 1);
+      if (L > K && L < npr) {
+        const int idx = (slot / Sh::kHalves) * NP + (slot % Sh::kHalves) * Sh::kClasses + cl;
+        if (idx < Sh::kTblEntries)
+          tbl[idx] = (unsigned)Sh::addr(2 * K + off, 2 * L + off) | ((unsigned)K << 16) | ((unsigned)L << 24);
+        ++slot;
+      }
+    }
+  }
 }
 
-// One step of the odd-even ordering.  SH = 0: pattern A, pairs (2K, 2K+1), K < m/2.
-// SH = -1: pattern B, pairs (2K-1, 2K), K <= m/2, pairs 0 and m/2 half phantom.
-template <typename T, int NP, bool EVECS, int SH>
-__device__ __forceinline__ void warp_step(T* __restrict__ M, T* __restrict__ cs,
-                                          const unsigned* __restrict__ tbl, T (&e)[EVECS ? NP : 1],
-                                          int m, int sub, int& n_rot) {
+// One step of the odd-even ordering.  OFF = 0: pattern A, pairs (2j, 2j+1), j < m/2.
+// OFF = 1: pattern B, pairs (2j+1, 2j+2), j < m/2 - 1; positions 0 and m-1 sit out.
+template <typename T, int NP, bool EVECS, int OFF>
+__device__ __forceinline__ void warp_step(T* __restrict__ M, T* __restrict__ cs, T* __restrict__ cc,
+                                          T* __restrict__ ss, const unsigned* __restrict__ tbl,
+                                          T (&e)[EVECS ? NP : 1], int m, int sub, int& n_rot) {
   using Sh = WarpShape<NP>;
   using T2 = typename Pair2<T>::type;
-  constexpr int kIt = (SH == 0) ? Sh::kItA : Sh::kItB;
-  const int np = (m >> 1) + (SH == 0 ? 0 : 1);
-  const int nblk = np * (np - 1) / 2;
+  const int npr = (m >> 1) - OFF;
   T2* cs2 = reinterpret_cast<T2*>(cs);
+  // offsets of the block's four elements from its first one (columns are even/odd split)
+  constexpr int o01 = (OFF == 0) ? Sh::kH : 1 - Sh::kH;
+  constexpr int o10 = Sh::kLd;
+  constexpr int o11 = Sh::kLd + o01;
 
   // ---- phase 1: one lane per pair -- skip test (:191), CalcRot (:233-256), the pair's
   // own 2x2 block (:337-338,347) with the two positions exchanged
-  if (sub < np) {
-    const int p = 2 * sub + SH, q = p + 1;
-    T c = T(1), s = T(0);
-    if (SH != 0 && p < 0) { c = T(0); s = T(-1); }        // (phantom, 0): keeps position 0
-    else if (SH != 0 && q >= m) { c = T(0); s = T(1); }   // (m-1, phantom): keeps position m-1
-    else {
-      T* pp = M + Sh::addr(p, p);
-      T* qq = M + Sh::addr(q, q);
-      T* pq = M + Sh::addr(p, q);
-      const T mpp = *pp, mqq = *qq, a = *pq;
-      T npp = mqq, nqq = mpp;
-      if (pair_needs_rotation(a, mpp, mqq)) {
-        const T d = mqq - mpp;
-        T t;
-        jacobi_rotation(d, a, rotation_range_unsafe(d, a), c, s, t);
-        const T g = t * a;
-        npp = mqq + g;
-        nqq = mpp - g;
-        *pq = T(0);
-        ++n_rot;
-      }
-      *pp = npp;
-      *qq = nqq;
+  if (sub < npr) {
+    const int p = 2 * sub + OFF;
+    T* pp = M + Sh::addr(p, p);
+    T* pq = pp + o01;                  // (p, p+1)
+    T* qq = pp + o11;                  // (p+1, p+1)
+    const T mpp = *pp, mqq = *qq, a = *pq;
+    T c = T(1), s = T(0), npp = mqq, nqq = mpp;
+    if (pair_needs_rotation(a, mpp, mqq)) {
+      const T d = mqq - mpp;
+      T t;
+      jacobi_rotation(d, a, rotation_range_unsafe(d, a), c, s, t);
+      const T g = t * a;
+      npp = mqq + g;
+      nqq = mpp - g;
+      *pq = T(0);
+      ++n_rot;
     }
+    *pp = npp;
+    *qq = nqq;
     T2 v; v.x = c; v.y = s;
     cs2[sub] = v;
+    cc[sub] = c;
+    ss[sub] = s;
   }
   __syncwarp();
 
   // ---- phase 2a: 2x2 blocks rows {pair K} x cols {pair L}, K < L:  B <- G_K B G_L^T with
   // G = [[s, c], [c, -s]] (ApplyRot :350-390 for both rotations, positions exchanged)
 #pragma unroll
-  for (int it = 0; it < kIt; ++it) {
-    const int f = it * NP + sub;
-    if (f < nblk) {
-      const unsigned ent = tbl[f];
+  for (int it = 0; it < Sh::kIt; ++it) {
+    const unsigned ent = tbl[it * NP + sub];
+    if (ent != 0xffffffffu) {
       T* b = M + (ent & 0xffffu);
-      const T2 rk = cs2[(ent >> 16) & 0xffu];
-      const T2 rl = cs2[ent >> 24];
-      constexpr int o00 = (SH == 0) ? Sh::kH : 0;
-      constexpr int o01 = (SH == 0) ? 1 : Sh::kH;
-      const T b00 = b[o00], b01 = b[o01], b10 = b[Sh::kLd + o00], b11 = b[Sh::kLd + o01];
-      const T ck = rk.x, sk = rk.y, cl = rl.x, sl = rl.y;
+      const int K = (ent >> 16) & 0xffu, L = ent >> 24;
+      const T ck = cc[K], sk = ss[K], cl = cc[L], sl = ss[L];
+      const T b00 = b[0], b01 = b[o01], b10 = b[o10], b11 = b[o11];
       const T u00 = jfma(sk, b00, ck * b10), u01 = jfma(sk, b01, ck * b11);
       const T u10 = jfma(ck, b00, -(sk * b10)), u11 = jfma(ck, b01, -(sk * b11));
-      b[o00] = jfma(sl, u00, cl * u01);
+      b[0] = jfma(sl, u00, cl * u01);
       b[o01] = jfma(cl, u00, -(sl * u01));
-      b[Sh::kLd + o00] = jfma(sl, u10, cl * u11);
-      b[Sh::kLd + o01] = jfma(cl, u10, -(sl * u11));
+      b[o10] = jfma(sl, u10, cl * u11);
+      b[o11] = jfma(cl, u10, -(sl * u11));
+    }
+  }
+  // ---- pattern B: the unpaired end positions.  Row 0 meets the column pair j (first half
+  // of the lanes), column m-1 meets the row pair j (second half); same 2-vector update.
+  if (OFF == 1) {
+    const int j = sub < NP / 2 ? sub : sub - NP / 2;
+    if (j < npr) {
+      T* x0 = (sub < NP / 2) ? M + Sh::addr(0, 2 * j + 1) : M + Sh::addr(2 * j + 1, m - 1);
+      T* x1 = (sub < NP / 2) ? x0 + o01 : x0 + o10;
+      const T c = cc[j], s = ss[j];
+      const T v0 = *x0, v1 = *x1;
+      *x0 = jfma(s, v0, c * v1);
+      *x1 = jfma(c, v0, -(s * v1));
     }
   }
   // ---- phase 2b: eigenvector rows (ApplyRotLeft :414-418), registers only
   if (EVECS) {
 #pragma unroll
-    for (int K = (SH == 0 ? 0 : 1); K < NP / 2; ++K) {
-      const int p = 2 * K + SH, q = p + 1;   // compile-time register names
-      if (K < np + SH) {                      // A: K < m/2   B: K <= m/2 - 1 (real pairs only)
-        const T2 r = cs2[K];
+    for (int j = 0; j < NP / 2 - OFF; ++j) {
+      const int p = 2 * j + OFF, q = p + 1;   // compile-time register names
+      if (j < npr) {
+        const T2 r = cs2[j];
         const T x = e[p], y = e[q];
         e[p] = jfma(r.y, x, r.x * y);
         e[q] = jfma(r.x, x, -(r.y * y));
@@ -185,26 +203,21 @@ jpd_warp_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict_
   const int grp = lane / NP, sub = lane % NP;
   const unsigned grp_mask = (NP == 32) ? 0xffffffffu : (((1u << NP) - 1u) << (grp * NP));
   const int m = n + (n & 1);
-  const int npA = m >> 1, npB = npA + 1;
 
-  // ---- block-wide tables: flat block index -> (offset of the block, K, L), both patterns
+  // ---- block-wide schedule tables, one per pattern
   unsigned* tblA = reinterpret_cast<unsigned*>(smem_raw);
-  unsigned* tblB = tblA + Sh::kBlkMaxA;
-  for (int f = threadIdx.x; f < npA * (npA - 1) / 2; f += blockDim.x) {
-    int K, L; tri_decode(f, npA, K, L);
-    tblA[f] = (unsigned)((2 * K + 1) * Sh::kLd + L) | ((unsigned)K << 16) | ((unsigned)L << 24);
-  }
-  for (int f = threadIdx.x; f < npB * (npB - 1) / 2; f += blockDim.x) {
-    int K, L; tri_decode(f, npB, K, L);
-    tblB[f] = (unsigned)((2 * K) * Sh::kLd + L) | ((unsigned)K << 16) | ((unsigned)L << 24);
-  }
+  unsigned* tblB = tblA + Sh::kTblEntries;
+  build_schedule<NP>(tblA, m >> 1, 0);
+  build_schedule<NP>(tblB, (m >> 1) - 1, 1);
   __syncthreads();
 
   unsigned char* gbase = smem_raw + Sh::table_bytes() + (size_t)(warp * G + grp) * Sh::group_bytes(sizeof(T));
   T* M = reinterpret_cast<T*>(gbase);
   T* cs = M + Sh::kMElems;
-  T* ev = cs + 2 * Sh::kPairsMax;
-  int* perm = reinterpret_cast<int*>(ev + NP + 2);
+  T* cc = cs + 2 * Sh::kPairsMax;
+  T* ss = cc + Sh::kPairsMax;
+  T* ev = ss + Sh::kPairsMax;
+  int* perm = reinterpret_cast<int*>(ev + NP);
 
   const long long b = ((long long)blockIdx.x * nwarps + warp) * G + grp;
   const bool live = b < batch;
@@ -246,8 +259,8 @@ jpd_warp_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict_
     need = (vote & grp_mask) != 0u;
     if (vote == 0u || sweeps >= max_num_sweeps) break;
     for (int step = 0; step < m; step += 2) {
-      warp_step<T, NP, EVECS, 0>(M, cs, tblA, e, m, sub, n_rot);
-      warp_step<T, NP, EVECS, -1>(M, cs, tblB, e, m, sub, n_rot);
+      warp_step<T, NP, EVECS, 0>(M, cs, cc, ss, tblA, e, m, sub, n_rot);
+      warp_step<T, NP, EVECS, 1>(M, cs, cc, ss, tblB, e, m, sub, n_rot);
     }
     ++sweeps;
   }
