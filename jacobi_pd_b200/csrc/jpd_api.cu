@@ -94,7 +94,9 @@ int launch_warp(const T* mat, T* evals, T* evecs, int* iters, int n, long long b
   const long long blocks = (batch + per_block - 1) / per_block;
   if (blocks > 0x7fffffffLL) return JPD_ERR_UNSUPPORTED;
   const size_t smem = Sh::block_bytes(sizeof(T), warps);
-  auto kernel = calc ? jpd_warp_kernel<T, NP, true> : jpd_warp_kernel<T, NP, false>;
+  const bool full = (n == NP);
+  auto kernel = calc ? (full ? jpd_warp_kernel<T, NP, true, true> : jpd_warp_kernel<T, NP, true, false>)
+                     : (full ? jpd_warp_kernel<T, NP, false, true> : jpd_warp_kernel<T, NP, false, false>);
   if (smem > 48 * 1024)
     JPD_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernel<<<dim3((unsigned)blocks), dim3(kWarpThreads), smem, st>>>(

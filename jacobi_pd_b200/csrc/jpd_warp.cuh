@@ -99,13 +99,13 @@ __device__ __forceinline__ void build_schedule(unsigned* tbl, int npr, int off) 
 
 // One step of the odd-even ordering.  OFF = 0: pattern A, pairs (2j, 2j+1), j < m/2.
 // OFF = 1: pattern B, pairs (2j+1, 2j+2), j < m/2 - 1; positions 0 and m-1 sit out.
-template <typename T, int NP, bool EVECS, int OFF>
+template <typename T, int NP, bool EVECS, int OFF, bool FULL>
 __device__ __forceinline__ void warp_step(T* __restrict__ M, T* __restrict__ cs, T* __restrict__ cc,
                                           T* __restrict__ ss, const unsigned* __restrict__ tbl,
                                           T (&e)[EVECS ? NP : 1], int m, int sub, int& n_rot) {
   using Sh = WarpShape<NP>;
   using T2 = typename Pair2<T>::type;
-  const int npr = (m >> 1) - OFF;
+  const int npr = FULL ? NP / 2 - OFF : (m >> 1) - OFF;   // FULL: m == NP, no runtime guards
   T2* cs2 = reinterpret_cast<T2*>(cs);
   // offsets of the block's four elements from its first one (columns are even/odd split)
   constexpr int o01 = (OFF == 0) ? Sh::kH : 1 - Sh::kH;
@@ -163,7 +163,7 @@ __device__ __forceinline__ void warp_step(T* __restrict__ M, T* __restrict__ cs,
   if (OFF == 1) {
     const int j = sub < NP / 2 ? sub : sub - NP / 2;
     if (j < npr) {
-      T* x0 = (sub < NP / 2) ? M + Sh::addr(0, 2 * j + 1) : M + Sh::addr(2 * j + 1, m - 1);
+      T* x0 = (sub < NP / 2) ? M + Sh::addr(0, 2 * j + 1) : M + Sh::addr(2 * j + 1, (FULL ? NP : m) - 1);
       T* x1 = (sub < NP / 2) ? x0 + o01 : x0 + o10;
       const T c = cc[j], s = ss[j];
       const T v0 = *x0, v1 = *x1;
@@ -176,7 +176,7 @@ __device__ __forceinline__ void warp_step(T* __restrict__ M, T* __restrict__ cs,
 #pragma unroll
     for (int j = 0; j < NP / 2 - OFF; ++j) {
       const int p = 2 * j + OFF, q = p + 1;   // compile-time register names
-      if (j < npr) {
+      if (FULL || j < npr) {
         const T2 r = cs2[j];
         const T x = e[p], y = e[q];
         e[p] = jfma(r.y, x, r.x * y);
@@ -190,9 +190,15 @@ __device__ __forceinline__ void warp_step(T* __restrict__ M, T* __restrict__ cs,
 #ifndef JPD_WARP_THREADS
 #define JPD_WARP_THREADS 128
 #endif
+// resident blocks per SM the register allocator is asked to make room for
+template <typename T, int NP> struct WarpLaunch {
+  static constexpr int kMinBlocks = sizeof(T) == 8 ? (NP == 32 ? 4 : (NP == 16 ? 7 : 8))
+                                                   : (NP == 32 ? 6 : 8);
+};
 
-template <typename T, int NP, bool EVECS>
-__global__ void __launch_bounds__(JPD_WARP_THREADS)
+// FULL: n == NP (even, no padding) -- every per-pair guard folds away at compile time
+template <typename T, int NP, bool EVECS, bool FULL>
+__global__ void __launch_bounds__(JPD_WARP_THREADS, (WarpLaunch<T, NP>::kMinBlocks))
 jpd_warp_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict__ evecs,
                 int* __restrict__ n_iters, int n, long long batch, int soa, int sort_criteria,
                 int max_num_sweeps) {
@@ -258,9 +264,9 @@ jpd_warp_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict_
     const unsigned vote = __ballot_sync(0xffffffffu, need);
     need = (vote & grp_mask) != 0u;
     if (vote == 0u || sweeps >= max_num_sweeps) break;
-    for (int step = 0; step < m; step += 2) {
-      warp_step<T, NP, EVECS, 0>(M, cs, cc, ss, tblA, e, m, sub, n_rot);
-      warp_step<T, NP, EVECS, 1>(M, cs, cc, ss, tblB, e, m, sub, n_rot);
+    for (int step = 0; step < (FULL ? NP : m); step += 2) {
+      warp_step<T, NP, EVECS, 0, FULL>(M, cs, cc, ss, tblA, e, m, sub, n_rot);
+      warp_step<T, NP, EVECS, 1, FULL>(M, cs, cc, ss, tblB, e, m, sub, n_rot);
     }
     ++sweeps;
   }
