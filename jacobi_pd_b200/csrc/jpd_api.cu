@@ -19,6 +19,7 @@
 #include "jpd_block.cuh"
 #include "jpd_small.cuh"
 #include "jpd_warp.cuh"
+#include "jpd_cta.cuh"
 
 namespace {
 
@@ -106,7 +107,34 @@ int launch_warp(const T* mat, T* evals, T* evecs, int* iters, int n, long long b
   return JPD_OK;
 }
 
-// ------------------------------------------------------------------ tier 3/4 plan + launch
+// ------------------------------------------------------------------ tier 3 launch (CTA per matrix, E in registers)
+constexpr int kCtaMaxN = 128;
+
+template <typename T, int NPB>
+int launch_cta(const T* mat, T* evals, T* evecs, int* iters, int n, long long batch, int layout,
+               int sort, int calc, int sweeps, cudaStream_t st) {
+  using Sh = CtaShape<NPB>;
+  int dev = 0;
+  JPD_CK(cudaGetDevice(&dev));
+  DeviceInfo info;
+  int rc = device_info(dev, &info);
+  if (rc != JPD_OK) return rc;
+  const size_t smem = Sh::block_bytes(sizeof(T));
+  auto kernel = calc ? jpd_cta_kernel<T, NPB, true> : jpd_cta_kernel<T, NPB, false>;
+  if (smem > 48 * 1024)
+    JPD_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  JPD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, Sh::kThreads, smem));
+  if (per_sm < 1) return JPD_ERR_UNSUPPORTED;
+  const long long grid = std::min<long long>(batch, (long long)per_sm * info.sm_count);
+  kernel<<<dim3((unsigned)grid), dim3(Sh::kThreads), smem, st>>>(
+      mat, evals, evecs, iters, n, batch, layout == JPD_LAYOUT_SOA ? 1 : 0, sort, sweeps);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  JPD_CK(cudaGetLastError());
+  return JPD_OK;
+}
+
+// ------------------------------------------------------------------ tier 4 plan + launch
 BlockPlan make_block_plan(int n, int elem, int calc, int smem_limit) {
   BlockPlan p{};
   const int m = n + (n & 1), half = m / 2;
@@ -195,6 +223,9 @@ int diagonalize_device(const T* mat, T* evals, T* evecs, int* iters, int n, long
   if (n <= 8) return launch_warp<T, 8>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
   if (n <= 16) return launch_warp<T, 16>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
   if (n <= kWarpMaxN) return launch_warp<T, 32>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
+  if (n <= 64) return launch_cta<T, 64>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
+  if (n <= 96) return launch_cta<T, 96>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
+  if (n <= kCtaMaxN) return launch_cta<T, 128>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
   return launch_block<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
 }
 
@@ -482,6 +513,7 @@ int jpd_kernel_tier(int n, int elem_size, int calc_evecs) {
   if (n < 1 || n > JPD_MAX_N || (elem_size != 4 && elem_size != 8)) return JPD_ERR_INVALID_ARG;
   if (n <= kSmallMaxN) return 1;
   if (n <= kWarpMaxN) return 2;
+  if (n <= kCtaMaxN) return 3;
   int limit = 232448, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) {
     DeviceInfo info;
@@ -490,7 +522,7 @@ int jpd_kernel_tier(int n, int elem_size, int calc_evecs) {
     (void)cudaGetLastError();
   }
   const BlockPlan p = make_block_plan(n, elem_size, calc_evecs ? 1 : 0, limit);
-  return (p.m_in_smem && p.e_in_smem) ? 3 : 4;
+  return 4;
 }
 
 long long jpd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
