@@ -173,20 +173,22 @@ def fp_peak(jpd, torch, elem=8):
 
 
 def side_workloads(jpd, torch, hbm_peak):
-    """The other sizes the metric names (n=3, n=32 fp64), device-resident, one GPU: context
-    lines inside the JSON, not the headline."""
+    """The other sizes the metric and the configs name (n=3 thread tier, n=16/32 warp tier,
+    n=128 CTA tier; fp64), device-resident, one GPU: context lines inside the JSON, not the
+    headline."""
     out = {}
     fp64_tflops = fp_peak(jpd, torch, 8)
     out["fp64_fma_peak_tflops_measured"] = round(fp64_tflops, 2)
     # mean rotations of the reference on these inputs (r_ref, SURVEY 8(d)) -> flop roofline
-    r_ref = {3: 8.71, 32: 2078.0}
-    for n, batch, layout in ((3, 1 << 23, jpd.LAYOUT_SOA), (32, 1 << 15, jpd.LAYOUT_AOS)):
+    r_ref = {3: 8.71, 16: 486.0, 32: 2078.0, 128: 35388.8}
+    cases = ((3, 1 << 23, jpd.LAYOUT_SOA, 5), (16, 1 << 18, jpd.LAYOUT_AOS, 5),
+             (32, 1 << 17, jpd.LAYOUT_AOS, 5), (128, 2048, jpd.LAYOUT_AOS, 2))
+    for n, batch, layout, reps in cases:
         shape = (n, n, batch) if layout == jpd.LAYOUT_SOA else (batch, n, n)
         m = torch.empty(shape, dtype=torch.float64, device="cuda")
         jpd.fill_synthetic(m, n, batch, layout, 0, 1234)
         res = jpd.diagonalize_batched(m, layout=layout)
         torch.cuda.synchronize()
-        reps = 5
         ms = time_device_steps(lambda: jpd.diagonalize_batched(m, layout=layout, out=res), reps, 3, lambda: None) / reps
         mats = batch / (ms * 1e-3)
         by = jpd.algorithmic_bytes(n, 8, True)
@@ -194,8 +196,8 @@ def side_workloads(jpd, torch, hbm_peak):
         fp_bound = fp64_tflops * 1e12 / (r_ref[n] * (12 * n + 4))
         bound = min(hbm_bound, fp_bound)
         out[f"n{n}_fp64"] = {
-            "batch": batch, "layout": "soa" if layout else "aos", "matrices_per_s": mats,
-            "ms_per_pass": ms, "bound": "hbm" if hbm_bound < fp_bound else "fp64",
+            "batch": batch, "layout": "soa" if layout else "aos", "tier": int(jpd.lib().jpd_kernel_tier(n, 8, 1)),
+            "matrices_per_s": mats, "ms_per_pass": ms, "bound": "hbm" if hbm_bound < fp_bound else "fp64",
             "roofline_matrices_per_s": bound, "frac": mats / bound,
             "failed": int((res[2] == 0).sum().item()),
         }
@@ -210,11 +212,17 @@ def cpu_reference_run(sample, passes):
     mat = ob.fill_synthetic(N_MAT, sample, 0, KIND_QUAT, SEED, 0, np.float64)
     fn = ob.ref_diagonalize if ob.ref_available() else ob.oracle_diagonalize
     kind = "reference" if ob.ref_available() else "port"
-    fn(mat[: min(sample, 100000)], SORT_DEC, True, MAX_SWEEPS, 0)  # warm
+    # all host cores this process may run on, stated explicitly: torchrun exports
+    # OMP_NUM_THREADS=1, which would otherwise pin the reference arm to one thread
+    try:
+        n_thr = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n_thr = os.cpu_count() or 1
+    fn(mat[: min(sample, 100000)], SORT_DEC, True, MAX_SWEEPS, n_thr)  # warm
     times, used, iters = [], 1, None
     for _ in range(passes):
         t0 = time.perf_counter()
-        ev, vec, iters, used = fn(mat, SORT_DEC, True, MAX_SWEEPS, 0)
+        ev, vec, iters, used = fn(mat, SORT_DEC, True, MAX_SWEEPS, n_thr)
         times.append(time.perf_counter() - t0)
     return {"times": times, "cores": used, "kind": kind, "sample": sample,
             "mean_n_iters": float(iters.mean())}

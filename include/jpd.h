@@ -110,6 +110,37 @@ JPD_API int jpd_diagonalize_batched_host_multi_f32(const float* h_mat, float* h_
                                            int max_num_sweeps, int n_devices,
                                            const int* devices);
 
+/* ---- fused producers for the two callers the reference names (README.md:124-128) -----
+ * The step before Diagonalize, done in registers by the thread-per-matrix kernel, so that
+ * the 3x3 / 4x4 matrix never exists in memory.  Device pointers,
+ * asynchronous on `cuda_stream`, same return codes and n_iters semantics as above.
+ *
+ * colvars optimal rotation: d_corr holds 3x3 correlation matrices C = sum_k x_k y_k^T,
+ * row-major (xx xy xz yx yy yz zx zy zz): AoS corr[b*9 + e] or SoA corr[e*batch + b].  The
+ * 4x4 overlap matrix S (Horn 1987; the formula of jpd_fill_synthetic kind 1) is
+ * diagonalised as Diagonalize(S, ..., SORT_DECREASING_EVALS) would (jacobi_pd.hpp:159-220).
+ *   all_eigenpairs == 0: d_lambda[b] = largest eigenvalue, d_quat = its eigenvector with
+ *                        q0 >= 0 (AoS quat[b*4 + v], SoA quat[v*batch + b])
+ *   all_eigenpairs != 0: d_lambda / d_quat = evals (4) / evecs (4x4, rows) exactly as
+ *                        jpd_diagonalize_batched would lay them out for n = 4 */
+JPD_API int jpd_quaternion_from_correlation_f64(const double* d_corr, double* d_lambda, double* d_quat,
+                                        int* d_n_iters, long long batch, int layout,
+                                        int all_eigenpairs, int max_num_sweeps, void* cuda_stream);
+JPD_API int jpd_quaternion_from_correlation_f32(const float* d_corr, float* d_lambda, float* d_quat,
+                                        int* d_n_iters, long long batch, int layout,
+                                        int all_eigenpairs, int max_num_sweeps, void* cuda_stream);
+/* LAMMPS rigid bodies: d_inertia6 holds (Ixx, Iyy, Izz, Iyz, Ixz, Ixy) per body (AoS
+ * in[b*6 + e] or SoA in[e*batch + b]).  Diagonalize(n = 3, SORT_DECREASING_EVALS), then the
+ * post-step of the caller: d_moments (3, decreasing), d_axes[i*3 + k] = component i of
+ * principal axis k (eigenvectors as COLUMNS), third axis flipped if needed so that
+ * (ex x ey) . ez > 0.  AoS axes[b*9 + i*3 + k], SoA axes[(i*3+k)*batch + b]. */
+JPD_API int jpd_principal_axes_f64(const double* d_inertia6, double* d_moments, double* d_axes,
+                           int* d_n_iters, long long batch, int layout, int max_num_sweeps,
+                           void* cuda_stream);
+JPD_API int jpd_principal_axes_f32(const float* d_inertia6, float* d_moments, float* d_axes,
+                           int* d_n_iters, long long batch, int layout, int max_num_sweeps,
+                           void* cuda_stream);
+
 /* slice g of G of a batch: first index and length (the partition used above) */
 JPD_API void jpd_slice(long long batch, int n_parts, int part, long long* first, long long* count);
 

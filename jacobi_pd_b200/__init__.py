@@ -7,12 +7,13 @@ the same C ABI.  The CPU oracle lives in ``oracle/`` and is never imported from 
 from .api import (DO_NOT_SORT, SORT_DECREASING_EVALS, SORT_INCREASING_EVALS,
                   SORT_DECREASING_ABS_EVALS, SORT_INCREASING_ABS_EVALS, LAYOUT_AOS, LAYOUT_SOA,
                   Jacobi, diagonalize_batched, diagonalize_batched_host, fill_synthetic,
-                  slice_of, algorithmic_bytes)
+                  slice_of, algorithmic_bytes, quaternion_from_correlation, principal_axes)
 from ._lib import JpdError, build, lib, LIB_PATH
 
 __all__ = [
     "DO_NOT_SORT", "SORT_DECREASING_EVALS", "SORT_INCREASING_EVALS", "SORT_DECREASING_ABS_EVALS",
     "SORT_INCREASING_ABS_EVALS", "LAYOUT_AOS", "LAYOUT_SOA", "Jacobi", "diagonalize_batched",
-    "diagonalize_batched_host", "fill_synthetic", "slice_of", "algorithmic_bytes", "JpdError",
+    "diagonalize_batched_host", "fill_synthetic", "slice_of", "algorithmic_bytes",
+    "quaternion_from_correlation", "principal_axes", "JpdError",
     "build", "lib", "LIB_PATH",
 ]

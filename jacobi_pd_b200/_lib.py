@@ -24,6 +24,10 @@ SIGNATURES = {
     "jpd_diagonalize_batched_host_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_int, c_int, c_int, c_int]),
     "jpd_diagonalize_batched_host_multi_f64": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "jpd_diagonalize_batched_host_multi_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "jpd_quaternion_from_correlation_f64": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_vp]),
+    "jpd_quaternion_from_correlation_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_vp]),
+    "jpd_principal_axes_f64": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp]),
+    "jpd_principal_axes_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp]),
     "jpd_slice": (None, [c_ll, c_int, c_int, ctypes.POINTER(c_ll), ctypes.POINTER(c_ll)]),
     "jpd_fill_synthetic_f64": (c_int, [c_vp, c_int, c_ll, c_int, c_int, c_ull, c_ll, c_vp]),
     "jpd_fill_synthetic_f32": (c_int, [c_vp, c_int, c_ll, c_int, c_int, c_ull, c_ll, c_vp]),

@@ -82,6 +82,59 @@ def diagonalize_batched(mat, n: int | None = None, layout: int = LAYOUT_AOS,
     return evals, evecs, iters
 
 
+def quaternion_from_correlation(corr, layout: int = LAYOUT_AOS, all_eigenpairs: bool = False,
+                                max_num_sweeps: int = 50, stream=None):
+    """colvars optimal-rotation path fused in one kernel: 3x3 correlation matrices (CUDA
+    tensor, AoS ``(batch, 9)``/``(batch, 3, 3)`` or SoA ``(9, batch)``) -> ``(lambda, quat,
+    n_iters)``; with ``all_eigenpairs`` the four eigenvalues (decreasing) and the 4x4
+    eigenvector rows of the overlap matrix, laid out as ``diagonalize_batched`` would."""
+    import torch
+    if not corr.is_cuda or not corr.is_contiguous():
+        raise _lib.JpdError("quaternion_from_correlation needs a contiguous CUDA tensor (no CPU fallback)")
+    batch = corr.shape[0] if layout == LAYOUT_AOS else corr.shape[-1]
+    if corr.numel() != 9 * batch:
+        raise ValueError("corr must hold 9 scalars per matrix")
+    sfx = _suffix(corr.dtype)
+    if all_eigenpairs:
+        es, vs = out_shapes(4, batch, layout)
+    else:
+        es, vs = ((batch,), (batch, 4)) if layout == LAYOUT_AOS else ((batch,), (4, batch))
+    lam = torch.empty(es, dtype=corr.dtype, device=corr.device)
+    quat = torch.empty(vs, dtype=corr.dtype, device=corr.device)
+    iters = torch.empty((batch,), dtype=torch.int32, device=corr.device)
+    st = torch.cuda.current_stream(corr.device).cuda_stream if stream is None else stream
+    with torch.cuda.device(corr.device):
+        rc = getattr(_lib.lib(), f"jpd_quaternion_from_correlation_{sfx}")(
+            corr.data_ptr(), lam.data_ptr(), quat.data_ptr(), iters.data_ptr(), batch, layout,
+            1 if all_eigenpairs else 0, max_num_sweeps, st)
+    _lib.check(rc, "jpd_quaternion_from_correlation")
+    return lam, quat, iters
+
+
+def principal_axes(inertia6, layout: int = LAYOUT_AOS, max_num_sweeps: int = 50, stream=None):
+    """LAMMPS rigid-body path fused in one kernel: (Ixx, Iyy, Izz, Iyz, Ixz, Ixy) per body
+    (CUDA tensor, AoS ``(batch, 6)`` or SoA ``(6, batch)``) -> ``(moments, axes, n_iters)``:
+    moments decreasing, ``axes[b, i, k]`` = component i of principal axis k, right-handed."""
+    import torch
+    if not inertia6.is_cuda or not inertia6.is_contiguous():
+        raise _lib.JpdError("principal_axes needs a contiguous CUDA tensor (no CPU fallback)")
+    batch = inertia6.shape[0] if layout == LAYOUT_AOS else inertia6.shape[-1]
+    if inertia6.numel() != 6 * batch:
+        raise ValueError("inertia6 must hold 6 scalars per body")
+    sfx = _suffix(inertia6.dtype)
+    es, vs = out_shapes(3, batch, layout)
+    mom = torch.empty(es, dtype=inertia6.dtype, device=inertia6.device)
+    axes = torch.empty(vs, dtype=inertia6.dtype, device=inertia6.device)
+    iters = torch.empty((batch,), dtype=torch.int32, device=inertia6.device)
+    st = torch.cuda.current_stream(inertia6.device).cuda_stream if stream is None else stream
+    with torch.cuda.device(inertia6.device):
+        rc = getattr(_lib.lib(), f"jpd_principal_axes_{sfx}")(
+            inertia6.data_ptr(), mom.data_ptr(), axes.data_ptr(), iters.data_ptr(), batch, layout,
+            max_num_sweeps, st)
+    _lib.check(rc, "jpd_principal_axes")
+    return mom, axes, iters
+
+
 def _host_ptr(a):
     if a is None:
         return None

@@ -20,6 +20,7 @@
 #include "jpd_small.cuh"
 #include "jpd_warp.cuh"
 #include "jpd_cta.cuh"
+#include "jpd_fused.cuh"
 
 namespace {
 
@@ -227,6 +228,47 @@ int diagonalize_device(const T* mat, T* evals, T* evecs, int* iters, int n, long
   if (n <= 96) return launch_cta<T, 96>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
   if (n <= kCtaMaxN) return launch_cta<T, 128>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
   return launch_block<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
+}
+
+// ------------------------------------------------------------------ fused producers
+template <typename T>
+int quaternion_device(const T* corr, T* lambda, T* quat, int* iters, long long batch, int layout,
+                      int all, int sweeps, cudaStream_t st) {
+  if (batch < 0 || (layout != JPD_LAYOUT_AOS && layout != JPD_LAYOUT_SOA)) return JPD_ERR_INVALID_ARG;
+  if (batch == 0) return JPD_OK;
+  if (!corr || !lambda || !quat) return JPD_ERR_INVALID_ARG;
+  if (sweeps < 0) sweeps = 0;
+  const long long blocks = (batch + kSmallThreads - 1) / kSmallThreads;
+  if (blocks > 0x7fffffffLL) return JPD_ERR_UNSUPPORTED;
+  const dim3 grid((unsigned)blocks), block(kSmallThreads);
+  const bool soa = layout == JPD_LAYOUT_SOA;
+  if (all) {
+    if (soa) jpd_quat_kernel<T, true, true><<<grid, block, 0, st>>>(corr, lambda, quat, iters, batch, sweeps);
+    else     jpd_quat_kernel<T, false, true><<<grid, block, 0, st>>>(corr, lambda, quat, iters, batch, sweeps);
+  } else {
+    if (soa) jpd_quat_kernel<T, true, false><<<grid, block, 0, st>>>(corr, lambda, quat, iters, batch, sweeps);
+    else     jpd_quat_kernel<T, false, false><<<grid, block, 0, st>>>(corr, lambda, quat, iters, batch, sweeps);
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  JPD_CK(cudaGetLastError());
+  return JPD_OK;
+}
+
+template <typename T>
+int principal_axes_device(const T* inertia6, T* moments, T* axes, int* iters, long long batch,
+                          int layout, int sweeps, cudaStream_t st) {
+  if (batch < 0 || (layout != JPD_LAYOUT_AOS && layout != JPD_LAYOUT_SOA)) return JPD_ERR_INVALID_ARG;
+  if (batch == 0) return JPD_OK;
+  if (!inertia6 || !moments || !axes) return JPD_ERR_INVALID_ARG;
+  if (sweeps < 0) sweeps = 0;
+  const long long blocks = (batch + kSmallThreads - 1) / kSmallThreads;
+  if (blocks > 0x7fffffffLL) return JPD_ERR_UNSUPPORTED;
+  const dim3 grid((unsigned)blocks), block(kSmallThreads);
+  if (layout == JPD_LAYOUT_SOA) jpd_inertia_kernel<T, true><<<grid, block, 0, st>>>(inertia6, moments, axes, iters, batch, sweeps);
+  else                          jpd_inertia_kernel<T, false><<<grid, block, 0, st>>>(inertia6, moments, axes, iters, batch, sweeps);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  JPD_CK(cudaGetLastError());
+  return JPD_OK;
 }
 
 // ------------------------------------------------------------------ host pipeline
@@ -470,6 +512,29 @@ int jpd_diagonalize_batched_host_multi_f32(const float* h_mat, float* h_evals, f
                                            int n_devices, const int* devices) {
   return diagonalize_host_multi<float>(h_mat, h_evals, h_evecs, h_n_iters, n, batch, layout,
                                        sort_criteria, calc_evecs ? 1 : 0, max_num_sweeps, n_devices, devices);
+}
+
+int jpd_quaternion_from_correlation_f64(const double* d_corr, double* d_lambda, double* d_quat, int* d_n_iters,
+                                        long long batch, int layout, int all_eigenpairs, int max_num_sweeps,
+                                        void* cuda_stream) {
+  return quaternion_device<double>(d_corr, d_lambda, d_quat, d_n_iters, batch, layout, all_eigenpairs,
+                                   max_num_sweeps, (cudaStream_t)cuda_stream);
+}
+int jpd_quaternion_from_correlation_f32(const float* d_corr, float* d_lambda, float* d_quat, int* d_n_iters,
+                                        long long batch, int layout, int all_eigenpairs, int max_num_sweeps,
+                                        void* cuda_stream) {
+  return quaternion_device<float>(d_corr, d_lambda, d_quat, d_n_iters, batch, layout, all_eigenpairs,
+                                  max_num_sweeps, (cudaStream_t)cuda_stream);
+}
+int jpd_principal_axes_f64(const double* d_inertia6, double* d_moments, double* d_axes, int* d_n_iters,
+                           long long batch, int layout, int max_num_sweeps, void* cuda_stream) {
+  return principal_axes_device<double>(d_inertia6, d_moments, d_axes, d_n_iters, batch, layout,
+                                       max_num_sweeps, (cudaStream_t)cuda_stream);
+}
+int jpd_principal_axes_f32(const float* d_inertia6, float* d_moments, float* d_axes, int* d_n_iters,
+                           long long batch, int layout, int max_num_sweeps, void* cuda_stream) {
+  return principal_axes_device<float>(d_inertia6, d_moments, d_axes, d_n_iters, batch, layout,
+                                      max_num_sweeps, (cudaStream_t)cuda_stream);
 }
 
 void jpd_slice(long long batch, int n_parts, int part, long long* first, long long* count) {
