@@ -56,6 +56,14 @@ template <> struct Abi<double> {
                         int sort, int calc, int sweeps, int n_dev, const int *devs) {
     return jpd_diagonalize_batched_host_multi_f64(m, ev, vec, it, n, b, layout, sort, calc, sweeps, n_dev, devs);
   }
+  static int quaternion(const double *c, double *lam, double *q, int *it, long long b, int layout, int all,
+                        int sweeps, void *stream) {
+    return jpd_quaternion_from_correlation_f64(c, lam, q, it, b, layout, all, sweeps, stream);
+  }
+  static int axes(const double *i6, double *mom, double *ax, int *it, long long b, int layout, int sweeps,
+                  void *stream) {
+    return jpd_principal_axes_f64(i6, mom, ax, it, b, layout, sweeps, stream);
+  }
 };
 template <> struct Abi<float> {
   static int device(const float *m, float *ev, float *vec, int *it, int n, long long b, int layout, int sort,
@@ -69,6 +77,14 @@ template <> struct Abi<float> {
   static int host_multi(const float *m, float *ev, float *vec, int *it, int n, long long b, int layout,
                         int sort, int calc, int sweeps, int n_dev, const int *devs) {
     return jpd_diagonalize_batched_host_multi_f32(m, ev, vec, it, n, b, layout, sort, calc, sweeps, n_dev, devs);
+  }
+  static int quaternion(const float *c, float *lam, float *q, int *it, long long b, int layout, int all,
+                        int sweeps, void *stream) {
+    return jpd_quaternion_from_correlation_f32(c, lam, q, it, b, layout, all, sweeps, stream);
+  }
+  static int axes(const float *i6, float *mom, float *ax, int *it, long long b, int layout, int sweeps,
+                  void *stream) {
+    return jpd_principal_axes_f32(i6, mom, ax, it, b, layout, sweeps, stream);
   }
 };
 
@@ -199,6 +215,30 @@ struct BatchedJacobi {
                                                  static_cast<int>(layout), sort_criteria, calc_evecs ? 1 : 0,
                                                  max_num_sweeps, n_devices, devices),
                   "jacobi_pd::BatchedJacobi::DiagonalizeHostMultiGpu");
+  }
+
+  /// colvars optimal rotation, fused: 3x3 correlation matrices (row-major, 9 scalars each) ->
+  /// largest eigenvalue of the 4x4 overlap matrix and its eigenvector, the rotation
+  /// quaternion (q0 >= 0); with all_eigenpairs the 4 eigenvalues (decreasing) and 4x4
+  /// eigenvector rows.  Device pointers, asynchronous on `cuda_stream` (include/jpd.h).
+  static void QuaternionFromCorrelation(const Scalar *d_corr, Scalar *d_lambda, Scalar *d_quat, int *d_n_iters,
+                                        long long batch, Layout layout = Layout::AoS,
+                                        bool all_eigenpairs = false, int max_num_sweeps = 50,
+                                        void *cuda_stream = nullptr) {
+    detail::check(detail::Abi<Scalar>::quaternion(d_corr, d_lambda, d_quat, d_n_iters, batch,
+                                                 static_cast<int>(layout), all_eigenpairs ? 1 : 0,
+                                                 max_num_sweeps, cuda_stream),
+                  "jacobi_pd::BatchedJacobi::QuaternionFromCorrelation");
+  }
+
+  /// LAMMPS rigid bodies, fused: (Ixx, Iyy, Izz, Iyz, Ixz, Ixy) per body -> principal moments
+  /// (decreasing) and a right-handed frame with the principal axes as COLUMNS.
+  static void PrincipalAxes(const Scalar *d_inertia6, Scalar *d_moments, Scalar *d_axes, int *d_n_iters,
+                            long long batch, Layout layout = Layout::AoS, int max_num_sweeps = 50,
+                            void *cuda_stream = nullptr) {
+    detail::check(detail::Abi<Scalar>::axes(d_inertia6, d_moments, d_axes, d_n_iters, batch,
+                                           static_cast<int>(layout), max_num_sweeps, cuda_stream),
+                  "jacobi_pd::BatchedJacobi::PrincipalAxes");
   }
 };
 

@@ -45,6 +45,12 @@ extern "C" {
 
 #define JPD_LAYOUT_AOS 0
 #define JPD_LAYOUT_SOA 1
+/* adapter-only layouts (jpd_convert_layout_*): upper triangle packed row-major,
+ * t(i,j) = i*n - i(i-1)/2 + (j-i), T = n(n+1)/2 scalars per matrix; and an array of
+ * device pointers to scattered row-major n x n matrices (source only) */
+#define JPD_LAYOUT_PACKED_AOS 2   /* m[b*T + t(i,j)]     */
+#define JPD_LAYOUT_PACKED_SOA 3   /* m[t(i,j)*batch + b] */
+#define JPD_LAYOUT_POINTERS 4     /* ((const S* const*)src)[b][i*n + j] */
 
 #define JPD_DO_NOT_SORT 0
 #define JPD_SORT_DECREASING_EVALS 1
@@ -140,6 +146,19 @@ JPD_API int jpd_principal_axes_f64(const double* d_inertia6, double* d_moments, 
 JPD_API int jpd_principal_axes_f32(const float* d_inertia6, float* d_moments, float* d_axes,
                            int* d_n_iters, long long batch, int layout, int max_num_sweeps,
                            void* cuda_stream);
+
+/* ---- layout adapters ---------------------------------------------------
+ * Converts a device-resident batch of n x n matrices between the layouts above with one
+ * tiled-transpose kernel (32 consecutive scalars per warp on both sides).  Sources: all five
+ * layouts; targets: 0..3.  A packed source is mirrored into the lower triangle of a full
+ * target; a packed target receives the upper triangle (as the reference reads only
+ * mat[i][j], j >= i, jacobi_pd.hpp:167-171).  Also transposes eigenvector outputs between
+ * AoS and SoA.  Callers holding packed or scattered matrices run it once in front of
+ * jpd_diagonalize_batched_*. */
+JPD_API int jpd_convert_layout_f64(const void* d_src, int src_layout, double* d_dst, int dst_layout,
+                           int n, long long batch, void* cuda_stream);
+JPD_API int jpd_convert_layout_f32(const void* d_src, int src_layout, float* d_dst, int dst_layout,
+                           int n, long long batch, void* cuda_stream);
 
 /* slice g of G of a batch: first index and length (the partition used above) */
 JPD_API void jpd_slice(long long batch, int n_parts, int part, long long* first, long long* count);

@@ -7,13 +7,15 @@ the same C ABI.  The CPU oracle lives in ``oracle/`` and is never imported from 
 from .api import (DO_NOT_SORT, SORT_DECREASING_EVALS, SORT_INCREASING_EVALS,
                   SORT_DECREASING_ABS_EVALS, SORT_INCREASING_ABS_EVALS, LAYOUT_AOS, LAYOUT_SOA,
                   Jacobi, diagonalize_batched, diagonalize_batched_host, fill_synthetic,
-                  slice_of, algorithmic_bytes, quaternion_from_correlation, principal_axes)
+                  slice_of, algorithmic_bytes, quaternion_from_correlation, principal_axes, convert_layout, layout_shape,
+                  LAYOUT_PACKED_AOS, LAYOUT_PACKED_SOA, LAYOUT_POINTERS)
 from ._lib import JpdError, build, lib, LIB_PATH
 
 __all__ = [
     "DO_NOT_SORT", "SORT_DECREASING_EVALS", "SORT_INCREASING_EVALS", "SORT_DECREASING_ABS_EVALS",
     "SORT_INCREASING_ABS_EVALS", "LAYOUT_AOS", "LAYOUT_SOA", "Jacobi", "diagonalize_batched",
     "diagonalize_batched_host", "fill_synthetic", "slice_of", "algorithmic_bytes",
-    "quaternion_from_correlation", "principal_axes", "JpdError",
+    "quaternion_from_correlation", "principal_axes", "convert_layout", "layout_shape",
+    "LAYOUT_PACKED_AOS", "LAYOUT_PACKED_SOA", "LAYOUT_POINTERS", "JpdError",
     "build", "lib", "LIB_PATH",
 ]

@@ -28,6 +28,8 @@ SIGNATURES = {
     "jpd_quaternion_from_correlation_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_vp]),
     "jpd_principal_axes_f64": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp]),
     "jpd_principal_axes_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp]),
+    "jpd_convert_layout_f64": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_ll, c_vp]),
+    "jpd_convert_layout_f32": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_ll, c_vp]),
     "jpd_slice": (None, [c_ll, c_int, c_int, ctypes.POINTER(c_ll), ctypes.POINTER(c_ll)]),
     "jpd_fill_synthetic_f64": (c_int, [c_vp, c_int, c_ll, c_int, c_int, c_ull, c_ll, c_vp]),
     "jpd_fill_synthetic_f32": (c_int, [c_vp, c_int, c_ll, c_int, c_int, c_ull, c_ll, c_vp]),

@@ -24,6 +24,9 @@ SORT_INCREASING_ABS_EVALS = 4
 
 LAYOUT_AOS = 0
 LAYOUT_SOA = 1
+LAYOUT_PACKED_AOS = 2   # adapter-only layouts, see include/jpd.h
+LAYOUT_PACKED_SOA = 3
+LAYOUT_POINTERS = 4
 
 
 def _suffix(dtype) -> str:
@@ -133,6 +136,30 @@ def principal_axes(inertia6, layout: int = LAYOUT_AOS, max_num_sweeps: int = 50,
             max_num_sweeps, st)
     _lib.check(rc, "jpd_principal_axes")
     return mom, axes, iters
+
+
+def layout_shape(n: int, batch: int, layout: int):
+    t = n * (n + 1) // 2
+    return {LAYOUT_AOS: (batch, n, n), LAYOUT_SOA: (n, n, batch), LAYOUT_PACKED_AOS: (batch, t),
+            LAYOUT_PACKED_SOA: (t, batch)}[layout]
+
+
+def convert_layout(src, src_layout: int, dst_layout: int, n: int, batch: int, dtype=None, stream=None):
+    """Layout adapter: CUDA tensor in `src_layout` (for LAYOUT_POINTERS an
+    int64 tensor of device addresses, `dtype` giving the scalar type) -> new tensor in
+    `dst_layout`; one tiled-transpose kernel."""
+    import torch
+    if not src.is_cuda or not src.is_contiguous():
+        raise _lib.JpdError("convert_layout needs a contiguous CUDA tensor (no CPU fallback)")
+    dt = dtype if src_layout == LAYOUT_POINTERS else src.dtype
+    sfx = _suffix(dt)
+    dst = torch.empty(layout_shape(n, batch, dst_layout), dtype=dt, device=src.device)
+    st = torch.cuda.current_stream(src.device).cuda_stream if stream is None else stream
+    with torch.cuda.device(src.device):
+        rc = getattr(_lib.lib(), f"jpd_convert_layout_{sfx}")(src.data_ptr(), src_layout, dst.data_ptr(),
+                                                              dst_layout, n, batch, st)
+    _lib.check(rc, "jpd_convert_layout")
+    return dst
 
 
 def _host_ptr(a):

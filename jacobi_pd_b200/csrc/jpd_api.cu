@@ -21,6 +21,7 @@
 #include "jpd_warp.cuh"
 #include "jpd_cta.cuh"
 #include "jpd_fused.cuh"
+#include "jpd_layout.cuh"
 
 namespace {
 
@@ -266,6 +267,24 @@ int principal_axes_device(const T* inertia6, T* moments, T* axes, int* iters, lo
   const dim3 grid((unsigned)blocks), block(kSmallThreads);
   if (layout == JPD_LAYOUT_SOA) jpd_inertia_kernel<T, true><<<grid, block, 0, st>>>(inertia6, moments, axes, iters, batch, sweeps);
   else                          jpd_inertia_kernel<T, false><<<grid, block, 0, st>>>(inertia6, moments, axes, iters, batch, sweeps);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  JPD_CK(cudaGetLastError());
+  return JPD_OK;
+}
+
+// ------------------------------------------------------------------ layout adapters
+template <typename T>
+int convert_layout(const void* src, int src_layout, T* dst, int dst_layout, int n, long long batch,
+                   cudaStream_t st) {
+  if (n < 1 || n > JPD_MAX_N || batch < 0) return JPD_ERR_INVALID_ARG;
+  if (src_layout < kLayoutAoS || src_layout > kLayoutPointers) return JPD_ERR_INVALID_ARG;
+  if (dst_layout < kLayoutAoS || dst_layout > kLayoutPackedSoA) return JPD_ERR_INVALID_ARG;
+  if (batch == 0) return JPD_OK;
+  if (!src || !dst) return JPD_ERR_INVALID_ARG;
+  const long long bx = (batch + 31) / 32;
+  const long long by = ((long long)n * n + 31) / 32;
+  if (bx > 0x7fffffffLL || by > 65535) return JPD_ERR_UNSUPPORTED;
+  jpd_convert_kernel<T><<<dim3((unsigned)bx, (unsigned)by), dim3(32, 8), 0, st>>>(src, src_layout, dst, dst_layout, n, batch);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   JPD_CK(cudaGetLastError());
   return JPD_OK;
@@ -535,6 +554,15 @@ int jpd_principal_axes_f32(const float* d_inertia6, float* d_moments, float* d_a
                            long long batch, int layout, int max_num_sweeps, void* cuda_stream) {
   return principal_axes_device<float>(d_inertia6, d_moments, d_axes, d_n_iters, batch, layout,
                                       max_num_sweeps, (cudaStream_t)cuda_stream);
+}
+
+int jpd_convert_layout_f64(const void* d_src, int src_layout, double* d_dst, int dst_layout, int n,
+                           long long batch, void* cuda_stream) {
+  return convert_layout<double>(d_src, src_layout, d_dst, dst_layout, n, batch, (cudaStream_t)cuda_stream);
+}
+int jpd_convert_layout_f32(const void* d_src, int src_layout, float* d_dst, int dst_layout, int n,
+                           long long batch, void* cuda_stream) {
+  return convert_layout<float>(d_src, src_layout, d_dst, dst_layout, n, batch, (cudaStream_t)cuda_stream);
 }
 
 void jpd_slice(long long batch, int n_parts, int part, long long* first, long long* count) {
