@@ -148,11 +148,22 @@ JPD_HD double rsqrt_seed(double x) {
   return 1.0 / std::sqrt(x);
 #endif
 }
+#if defined(__CUDACC__)
+// 3/8 as a constant-bank operand: an FP64 instruction takes one immediate, and a literal
+// here makes ptxas re-materialise the second constant with two MOVs per use (r1 SASS: ~7
+// of the 76 instructions of a rotation); c[bank][offset] operands cost nothing.
+static __constant__ double jpd_c_three_eighths = 0.375;
+static __constant__ double jpd_c_half = 0.5;
+#endif
 JPD_HD double rsqrt_correct(double x, double y0) {
 #if defined(__CUDA_ARCH__)
   double xy = x * y0;
   double e = __fma_rn(-xy, y0, 1.0);       // 1 - x*y0^2, |e| <~ 2^-21
+#if defined(JPD_NO_CONST_BANK)
   double r = __fma_rn(0.375, e, 0.5);      // 1/2 + 3/8 e
+#else
+  double r = __fma_rn(jpd_c_three_eighths, e, 0.5);
+#endif
   double ey = e * y0;
   return __fma_rn(r, ey, y0);              // y0 (1 + e/2 + 3/8 e^2)
 #else
@@ -179,6 +190,15 @@ JPD_HD float rsqrt_correct(float x, float y0) {
   return y0;
 #endif
 }
+// 1/2 as a multiplier operand (constant bank on the device, see above)
+JPD_HD double half_const(double) {
+#if defined(__CUDA_ARCH__) && !defined(JPD_NO_CONST_BANK)
+  return jpd_c_half;
+#else
+  return 0.5;
+#endif
+}
+JPD_HD float half_const(float) { return 0.5f; }
 JPD_HD double rsqrt_refined(double x) { return rsqrt_correct(x, rsqrt_seed(x)); }
 JPD_HD float rsqrt_refined(float x) { return rsqrt_correct(x, rsqrt_seed(x)); }
 

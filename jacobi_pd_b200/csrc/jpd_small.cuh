@@ -121,10 +121,11 @@ JPD_HD void small_rotate_pair(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N 
                               (unsigned)((SmallRange<T>::kXMax - SmallRange<T>::kXMin) << KeyShift<T>::value));
   const bool need = flagged & x_ok;
   guard_hit = guard_hit | (flagged & !x_ok);
+#if defined(JPD_SELECT_CST)
   const T p = rsqrt_refined(x);
   const T rho = jabs(d) * p;
   const T ap = xor_sign(as * p, sign_src);         // sin(2 theta) / 2 with the sign of t
-  const T v = jfma(T(0.5), rho, T(0.5));           // cos^2(theta)
+  const T v = jfma(half_const(T(0)), rho, T(0.5));  // cos^2(theta)
   const T u = rsqrt_refined(v);
   T c = v * u;
   T s = ap * u;
@@ -132,6 +133,20 @@ JPD_HD void small_rotate_pair(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N 
   c = need ? c : T(1);
   s = need ? s : T(0);
   t = need ? t : T(0);
+#else
+  // A pair that is left alone gets the exact identity through TWO selects: p = 0 makes
+  // rho = 0, v = 1/2 (finite whatever x was), s = t = (a * 0) * u = 0, and c is replaced by 1.
+  T p = rsqrt_refined(x);
+  p = need ? p : T(0);
+  const T rho = jabs(d) * p;
+  const T ap = xor_sign(as * p, sign_src);         // sin(2 theta) / 2 with the sign of t
+  const T v = jfma(half_const(T(0)), rho, T(0.5));  // cos^2(theta)
+  const T u = rsqrt_refined(v);
+  T c = v * u;
+  const T s = ap * u;
+  const T t = s * u;
+  c = need ? c : T(1);
+#endif
   n_rot += need ? 1 : 0;
   // diagonal through t, pivot zeroed: jacobi_pd.hpp:337-338,347
   m[Sh::tri(I, I)] = jfma(-t, a, mii);
