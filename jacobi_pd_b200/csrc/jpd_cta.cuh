@@ -238,7 +238,8 @@ jpd_cta_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict__
       }
       ++sweeps;
     }
-    const bool converged = !need;
+    // max_num_sweeps == 0: the reference reports failure for n > 1 whatever the matrix (:185-186, :214-219)
+    const bool converged = !need && max_num_sweeps > 0;
     if (n_rot) atomicAdd(rot_total, n_rot);
 
     // ---- eigenvalues (:207-209); a sweep reverses the order of the positions
