@@ -92,10 +92,56 @@ JPD_HD bool key_needs_rotation(int ka, bool a_is_zero, int kii, int kjj) {
   return !a_is_zero & (ka > lowered);
 }
 
+// Rows I and J of E, column W onwards, using what is known about the entries at compile time.
+template <int N, typename T, int I, int J, unsigned long long NZ, unsigned long long ONE, int W>
+JPD_HD void small_rotate_rows(T (&e)[N * N], T c, T s) {
+  if constexpr (W < N) {
+    constexpr bool xi = (NZ >> (I * N + W)) & 1ull, yj = (NZ >> (J * N + W)) & 1ull;
+    constexpr bool x1 = (ONE >> (I * N + W)) & 1ull, y1 = (ONE >> (J * N + W)) & 1ull;
+    if constexpr (xi && yj) {
+      const T xx = e[I * N + W], yy = e[J * N + W];
+      e[I * N + W] = jfma(c, xx, -(s * yy));
+      e[J * N + W] = jfma(s, xx, c * yy);
+    } else if constexpr (xi) {          // E_J entry is 0
+      if constexpr (x1) { e[I * N + W] = c; e[J * N + W] = s; }
+      else { const T xx = e[I * N + W]; e[I * N + W] = c * xx; e[J * N + W] = s * xx; }
+    } else if constexpr (yj) {          // E_I entry is 0
+      if constexpr (y1) { e[I * N + W] = -s; e[J * N + W] = c; }
+      else { const T yy = e[J * N + W]; e[I * N + W] = -(s * yy); e[J * N + W] = c * yy; }
+    }
+    small_rotate_rows<N, T, I, J, NZ, ONE, W + 1>(e, c, s);
+  }
+}
+
 // One Jacobi rotation of the static pair (I,J), I<J, branch-free.  The skip test is taken
 // on the CURRENT entries (re-using the sweep-start flags instead was measured: stale flags
 // cost ~4% more rotations and a longer warp-max sweep count).
-template <int N, typename T, bool EVECS, bool SCALED, int I, int J>
+//
+// NZ / ONE: compile-time knowledge about E during the FIRST sweep, which starts from the
+// identity (bit i*N+w set = entry (i,w) may be nonzero / is exactly 1).  Rows that are still
+// unit vectors or sparse get their rotation with 0 or 2 multiplications per column instead
+// of 4 FP64 instructions (n = 4: 48 instead of 96 for the sweep).  Later sweeps pass
+// kDenseMask and compile to the plain update.
+constexpr unsigned long long kDenseMask = ~0ull;
+template <int N> JPD_CX constexpr unsigned long long identity_mask() {
+  unsigned long long mk = 0;
+  for (int i = 0; i < N; ++i) mk |= 1ull << (i * N + i);
+  return mk;
+}
+// masks after rows I and J have been combined
+template <int N> JPD_CX constexpr unsigned long long mask_after_nz(unsigned long long nz, int I, int J) {
+  for (int w = 0; w < N; ++w) {
+    const unsigned long long any = ((nz >> (I * N + w)) | (nz >> (J * N + w))) & 1ull;
+    nz = (nz & ~((1ull << (I * N + w)) | (1ull << (J * N + w)))) | (any << (I * N + w)) | (any << (J * N + w));
+  }
+  return nz;
+}
+template <int N> JPD_CX constexpr unsigned long long mask_after_one(unsigned long long one, int I, int J) {
+  for (int w = 0; w < N; ++w) one &= ~((1ull << (I * N + w)) | (1ull << (J * N + w)));
+  return one;
+}
+
+template <int N, typename T, bool EVECS, bool SCALED, int I, int J, unsigned long long NZ, unsigned long long ONE>
 JPD_HD void small_rotate_pair(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N : 1],
                               int& n_rot, bool& guard_hit) {
   using Sh = SmallShape<N>;
@@ -163,27 +209,26 @@ JPD_HD void small_rotate_pair(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N 
     m[kj] = jfma(s, xx, c * yy);
   }
   // eigenvector rows I and J: jacobi_pd.hpp:414-418
-  if (EVECS) {
-#pragma unroll
-    for (int w = 0; w < N; ++w) {
-      const T xx = e[I * N + w], yy = e[J * N + w];
-      e[I * N + w] = jfma(c, xx, -(s * yy));
-      e[J * N + w] = jfma(s, xx, c * yy);
-    }
-  }
+  if constexpr (EVECS) small_rotate_rows<N, T, I, J, NZ, ONE, 0>(e, c, s);
 }
 
 // One full round-robin sweep, unrolled at compile time: pair P of kSteps*kHalf.
-template <int N, typename T, bool EVECS, bool SCALED, int P>
+template <int N, typename T, bool EVECS, bool SCALED, int P, unsigned long long NZ = kDenseMask,
+          unsigned long long ONE = 0ull>
 JPD_HD void small_sweep_from(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N : 1],
                              int& n_rot, bool& guard_hit) {
   using Sh = SmallShape<N>;
   if constexpr (P < Sh::kSteps * Sh::kHalf) {
     constexpr int S = P / Sh::kHalf, K = P % Sh::kHalf;
     constexpr int A = Sh::player_a(S, K), B = Sh::player_b(S, K);
-    if constexpr (A < N && B < N)  // a pair with the dummy player (odd N) sits out
-      small_rotate_pair<N, T, EVECS, SCALED, (A < B ? A : B), (A < B ? B : A)>(m, e, n_rot, guard_hit);
-    small_sweep_from<N, T, EVECS, SCALED, P + 1>(m, e, n_rot, guard_hit);
+    if constexpr (A < N && B < N) {  // a pair with the dummy player (odd N) sits out
+      constexpr int I = A < B ? A : B, J = A < B ? B : A;
+      small_rotate_pair<N, T, EVECS, SCALED, I, J, NZ, ONE>(m, e, n_rot, guard_hit);
+      small_sweep_from<N, T, EVECS, SCALED, P + 1, mask_after_nz<N>(NZ, I, J), mask_after_one<N>(ONE, I, J)>(
+          m, e, n_rot, guard_hit);
+    } else {
+      small_sweep_from<N, T, EVECS, SCALED, P + 1, NZ, ONE>(m, e, n_rot, guard_hit);
+    }
   }
 }
 
@@ -227,7 +272,13 @@ JPD_HD int small_solve(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N : 1], i
     converged = converged || !any_need;
     if (!JPD_WARP_ANY(any_need)) break;
     bool guard_hit = false;
+#if defined(JPD_NO_FIRST_SWEEP_SPARSITY)
     if (rescale) small_sweep_from<N, T, EVECS, true, 0>(m, e, n_rot, guard_hit);
+#else
+    // sweep 0 starts from E = I (and `rescale` is still false): sparse eigenvector update
+    if (sweep == 0) small_sweep_from<N, T, EVECS, false, 0, identity_mask<N>(), identity_mask<N>()>(m, e, n_rot, guard_hit);
+    else if (rescale) small_sweep_from<N, T, EVECS, true, 0>(m, e, n_rot, guard_hit);
+#endif
     else         small_sweep_from<N, T, EVECS, false, 0>(m, e, n_rot, guard_hit);
     rescale = rescale || JPD_WARP_ANY(guard_hit);
   }
