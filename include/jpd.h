@@ -185,7 +185,8 @@ JPD_API long long jpd_fma_probe(int elem_size, int blocks, int threads, int iter
 JPD_API long long jpd_algorithmic_bytes(int n, int elem_size, int calc_evecs);
 /* which kernel tier the dispatcher picks: 1 thread/matrix (n <= 6), 2 warp/matrix
  * (n <= 32), 3 block/matrix with E in registers and M in shared memory (n <= 128),
- * 4 block/matrix with a global (L2-resident) workspace; negative on error */
+ * 4 four-CTA cluster/matrix with M in distributed shared memory (n <= 256), 5 block/matrix
+ * with a global (L2-resident) workspace (n <= JPD_MAX_N); negative on error */
 JPD_API int jpd_kernel_tier(int n, int elem_size, int calc_evecs);
 /* number of kernels launched by this library in this process so far */
 JPD_API long long jpd_launch_count(void);

@@ -20,6 +20,7 @@
 #include "jpd_small.cuh"
 #include "jpd_warp.cuh"
 #include "jpd_cta.cuh"
+#include "jpd_cluster.cuh"
 #include "jpd_fused.cuh"
 #include "jpd_layout.cuh"
 
@@ -136,7 +137,40 @@ int launch_cta(const T* mat, T* evals, T* evecs, int* iters, int n, long long ba
   return JPD_OK;
 }
 
-// ------------------------------------------------------------------ tier 4 plan + launch
+// ------------------------------------------------------------------ tier 4 launch (4-CTA cluster per matrix)
+constexpr int kClusterMaxN = ClusterShape::kN;
+
+template <typename T>
+int launch_cluster(const T* mat, T* evals, T* evecs, int* iters, int n, long long batch, int layout,
+                   int sort, int calc, int sweeps, cudaStream_t st) {
+  using Sh = ClusterShape;
+  const size_t smem = Sh::block_bytes(sizeof(T));
+  auto kernel = calc ? jpd_cluster_kernel<T, true> : jpd_cluster_kernel<T, false>;
+  JPD_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int max_clusters = 0;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(Sh::kCtas * 64);
+    cfg.blockDim = dim3(Sh::kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = Sh::kCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess || max_clusters < 1) {
+      (void)cudaGetLastError();
+      max_clusters = 32;
+    }
+  }
+  const long long clusters = std::min<long long>(batch, max_clusters);
+  kernel<<<dim3((unsigned)(clusters * Sh::kCtas)), dim3(Sh::kThreads), smem, st>>>(
+      mat, evals, evecs, iters, n, batch, layout == JPD_LAYOUT_SOA ? 1 : 0, sort, sweeps);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  JPD_CK(cudaGetLastError());
+  return JPD_OK;
+}
+
+// ------------------------------------------------------------------ tier 5 plan + launch
 BlockPlan make_block_plan(int n, int elem, int calc, int smem_limit) {
   BlockPlan p{};
   const int m = n + (n & 1), half = m / 2;
@@ -228,6 +262,7 @@ int diagonalize_device(const T* mat, T* evals, T* evecs, int* iters, int n, long
   if (n <= 64) return launch_cta<T, 64>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
   if (n <= 96) return launch_cta<T, 96>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
   if (n <= kCtaMaxN) return launch_cta<T, 128>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
+  if (n <= kClusterMaxN) return launch_cluster<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
   return launch_block<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
 }
 
@@ -607,6 +642,7 @@ int jpd_kernel_tier(int n, int elem_size, int calc_evecs) {
   if (n <= kSmallMaxN) return 1;
   if (n <= kWarpMaxN) return 2;
   if (n <= kCtaMaxN) return 3;
+  if (n <= kClusterMaxN) return 4;
   int limit = 232448, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) {
     DeviceInfo info;
@@ -615,7 +651,7 @@ int jpd_kernel_tier(int n, int elem_size, int calc_evecs) {
     (void)cudaGetLastError();
   }
   const BlockPlan p = make_block_plan(n, elem_size, calc_evecs ? 1 : 0, limit);
-  return 4;
+  return 5;
 }
 
 long long jpd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

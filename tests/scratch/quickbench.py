@@ -1,6 +1,6 @@
 import sys, time; sys.path.insert(0,'.')
 import torch, jacobi_pd_b200 as jpd
-cases = ((4, 1<<24, 1, torch.float64), (3, 1<<23, 0, torch.float64), (8, 1<<18, 0, torch.float64), (16, 1<<18, 0, torch.float64), (16, 1<<18, 0, torch.float32), (32, 1<<17, 0, torch.float64), (32, 1<<17, 0, torch.float32), (48, 8192, 0, torch.float64), (64, 8192, 0, torch.float64), (64, 8192, 0, torch.float32), (96, 2048, 0, torch.float64), (128, 2048, 0, torch.float64), (128, 2048, 0, torch.float32), (256, 256, 0, torch.float64))
+cases = ((4, 1<<24, 1, torch.float64), (3, 1<<23, 0, torch.float64), (8, 1<<18, 0, torch.float64), (16, 1<<18, 0, torch.float64), (16, 1<<18, 0, torch.float32), (32, 1<<17, 0, torch.float64), (32, 1<<17, 0, torch.float32), (48, 8192, 0, torch.float64), (64, 8192, 0, torch.float64), (64, 8192, 0, torch.float32), (96, 2048, 0, torch.float64), (128, 2048, 0, torch.float64), (128, 2048, 0, torch.float32), (200, 512, 0, torch.float64), (256, 512, 0, torch.float64), (256, 512, 0, torch.float32))
 if len(sys.argv) > 1:
     want = set(int(x) for x in sys.argv[1].split(','))
     cases = [c for c in cases if c[0] in want]

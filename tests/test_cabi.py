@@ -72,7 +72,7 @@ def test_byte_model_and_tiers():
     assert jpd.algorithmic_bytes(4, 8, False) == 244 - 128
     l = jpd.lib()
     assert [l.jpd_kernel_tier(n, 8, 1) for n in (1, 3, 4, 6)] == [1, 1, 1, 1]
-    assert l.jpd_kernel_tier(32, 8, 1) == 2 and l.jpd_kernel_tier(64, 8, 1) == 3 and l.jpd_kernel_tier(128, 8, 1) == 3 and l.jpd_kernel_tier(256, 8, 1) == 4
+    assert l.jpd_kernel_tier(32, 8, 1) == 2 and l.jpd_kernel_tier(64, 8, 1) == 3 and l.jpd_kernel_tier(128, 8, 1) == 3 and l.jpd_kernel_tier(129, 8, 1) == 4 and l.jpd_kernel_tier(256, 8, 1) == 4 and l.jpd_kernel_tier(257, 8, 1) == 5
 
 
 def test_no_silent_cpu_fallback():
