@@ -31,7 +31,7 @@ def test_parity_uniform(n, dtype):
         parity.full_check(A, out, ref, 1)
 
 
-@pytest.mark.parametrize("n", [2, 3, 4, 5, 8, 20, 33])
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 8, 20, 33, 130])
 @pytest.mark.parametrize("sort", [0, 1, 2, 3, 4])
 def test_all_sort_criteria(n, sort):
     A = ob.fill_synthetic(n, 512 if n <= 6 else 64, seed=77 + n)
@@ -40,7 +40,7 @@ def test_all_sort_criteria(n, sort):
     parity.full_check(A, out, ref, sort)
 
 
-@pytest.mark.parametrize("n", [3, 4, 6, 16, 40])
+@pytest.mark.parametrize("n", [3, 4, 6, 16, 40, 160])
 def test_no_evecs_and_sweep_limits(n):
     A = ob.fill_synthetic(n, 300, seed=5 + n)
     ref = ob.oracle_diagonalize(A, 1)
@@ -55,12 +55,28 @@ def test_no_evecs_and_sweep_limits(n):
     assert np.array_equal(ev0, ref0[0]) and np.array_equal(vec0, ref0[1])
 
 
-@pytest.mark.parametrize("n", [128, 256])
-def test_parity_large(n):
-    A = ob.fill_synthetic(n, 4 if n == 128 else 2, seed=9000 + n)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [96, 128, 129, 200, 255, 256])
+def test_parity_large(n, dtype):
+    """tier 3 (CTA) up to 128, tier 4 (4-CTA cluster, M in distributed shared memory) up to 256;
+    more matrices than resident clusters so that the persistent loop is exercised"""
+    A = ob.fill_synthetic(n, 5 if n <= 128 else 36, seed=9000 + n, dtype=dtype)
     ref = ob.oracle_diagonalize(A, 1)
-    out = run_gpu(A, 1)
-    parity.full_check(A, out, ref, 1)
+    for layout in (0, 1):
+        out = run_gpu(A, 1, layout=layout)
+        parity.full_check(A, out, ref, 1)
+    out2 = run_gpu(A, 1)                       # repeatable bit for bit (no cross-CTA race)
+    for x, y in zip(out, out2):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("n", [257, 300])
+def test_parity_beyond_cluster_tier(n):
+    rng = np.random.default_rng(9000 + n)        # (the counter generator stops at n = 256)
+    A = rng.uniform(-1, 1, (2, n, n))
+    A = np.ascontiguousarray(np.triu(A) + np.triu(A, 1).swapaxes(1, 2))
+    ref = ob.oracle_diagonalize(A, 1)
+    parity.full_check(A, run_gpu(A, 1), ref, 1)
 
 
 def test_host_api_matches_device_api():
