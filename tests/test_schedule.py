@@ -74,3 +74,63 @@ def test_schedule_tables_cover_every_block_once_without_bank_conflicts(NP):
                     for delta in (0, o01, sh["kld"], sh["kld"] + o01):
                         banks = [(a + delta) % 16 for a in ads]
                         assert len(set(banks)) == len(banks)
+
+
+# ---- tier 4 (jpd_cluster.cuh): snake ownership of 16-row groups, per-CTA schedule tables
+def cl_owner(r):
+    g = (r >> 4) & 3
+    return 3 - g if (r >> 6) & 1 else g
+
+
+def cl_lrow(r):
+    return ((r >> 6) << 4) | (r & 15)
+
+
+def cl_grow(lr, rank):
+    sg = lr >> 4
+    return 64 * sg + 16 * ((3 - rank) if sg & 1 else rank) + (lr & 15)
+
+
+def cl_pair_of(t, rank):
+    sg = t >> 3
+    return 8 * (4 * sg + ((3 - rank) if sg & 1 else rank)) + (t & 7)
+
+
+def test_cluster_ownership_maps_are_consistent():
+    for rank in range(4):
+        rows = [cl_grow(lr, rank) for lr in range(64)]
+        assert all(cl_owner(r) == rank and cl_lrow(r) == lr for lr, r in enumerate(rows))
+    assert sorted(cl_grow(lr, rank) for rank in range(4) for lr in range(64)) == list(range(256))
+    for off in (0, 1):      # every pair is handled by exactly one pivot quad, in the CTA owning its first row
+        pairs = sorted((cl_pair_of(t, rank), rank) for rank in range(4) for t in range(32))
+        assert [p for p, _ in pairs] == list(range(128))
+        assert all(cl_owner(2 * j + off) == rank for j, rank in pairs if 2 * j + off < 256)
+
+
+@pytest.mark.parametrize("n", [129, 130, 160, 200, 255, 256])
+def test_cluster_schedule_tables(n):
+    m = n + (n & 1)
+    for off, npr in ((0, m // 2), (1, m // 2 - 1)):
+        seen = []
+        for rank in range(4):
+            used = set()
+            for cl in range(16):
+                slot = 0
+                for K in range(npr):
+                    if cl_owner(2 * K + off) != rank:
+                        continue
+                    L = (cl - 6 * (K & 7)) % 16
+                    while L < npr:
+                        if L > K:
+                            idx = (slot >> 5) * 512 + (slot & 31) * 16 + cl
+                            assert idx < 4 * 512, "schedule table overflow"
+                            assert idx not in used
+                            used.add(idx)
+                            seen.append((K, L))
+                            slot += 1
+                        L += 16
+        assert sorted(seen) == sorted(itertools.combinations(range(npr), 2))
+    if n == 256:   # perfectly balanced at the design size
+        for rank in range(4):
+            cnt = sum(1 for K in range(128) if cl_owner(2 * K) == rank for L in range(K + 1, 128))
+            assert cnt == 2032
