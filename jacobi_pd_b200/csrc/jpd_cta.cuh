@@ -32,7 +32,7 @@ template <int NPB> struct CtaShape {
   static constexpr int kIt = 4;                       // block iterations per step (both patterns)
   static constexpr int kTblEntries = kIt * kThreads;
   // elements of T: M | (c,s) interleaved | c | s | eigenvalues | chunk-boundary rows (lo, hi)
-  static constexpr int kElems = kMElems + 4 * kPairsMax + NPB + 2 * kChunks * NPB;
+  static constexpr int kElems = kMElems + 2 * 4 * kPairsMax + NPB + 2 * kChunks * NPB;   // (c,s) arrays x2 (by pattern)
   JPD_CX static constexpr size_t table_bytes() { return (size_t)2 * kTblEntries * sizeof(unsigned); }
   JPD_CX static constexpr size_t block_bytes(size_t elem) {
     return table_bytes() + ((size_t)kElems * elem + 15) / 16 * 16 + (size_t)(NPB + 4) * sizeof(int);
@@ -65,29 +65,24 @@ __device__ __forceinline__ void cta_build_schedule(unsigned* tbl, int npr, int o
   }
 }
 
-template <typename T, int NPB, bool EVECS, int OFF>
-__device__ __forceinline__ void cta_step(T* __restrict__ M, T* __restrict__ cs, T* __restrict__ cc,
-                                         T* __restrict__ ss, T* __restrict__ xlo, T* __restrict__ xhi,
-                                         const unsigned* __restrict__ tbl, T (&e)[EVECS ? 32 : 1],
-                                         int m, int v, int ch, int& n_rot) {
+template <typename T> struct CtaCtx {
+  T* M; T* cs; T* cc; T* ss; T* xlo; T* xhi;     // cs/cc/ss: two buffers each, indexed by pattern
+  const unsigned* tblA; const unsigned* tblB;
+  int m, v, ch;
+};
+
+// ---- phase 1: one thread per pair (skip test :191, CalcRot :233-256, own 2x2 block)
+template <typename T, int NPB, int OFF>
+__device__ __forceinline__ void cta_pivot(const CtaCtx<T>& cx, int& n_rot) {
   using Sh = CtaShape<NPB>;
   using T2 = typename Pair2<T>::type;
-  const int tid = threadIdx.x;
-  const int npr = (m >> 1) - OFF;
-  T2* cs2 = reinterpret_cast<T2*>(cs);
   constexpr int o01 = (OFF == 0) ? Sh::kH : 1 - Sh::kH;
-  constexpr int o10 = Sh::kLd;
   constexpr int o11 = Sh::kLd + o01;
-
-  // ---- pattern B: publish the rows that pair across a chunk boundary
-  if (EVECS && OFF == 1) {
-    if (ch > 0) xlo[ch * NPB + v] = e[0];
-    if (ch < Sh::kChunks - 1) xhi[ch * NPB + v] = e[31];
-  }
-  // ---- phase 1: one thread per pair (skip test :191, CalcRot :233-256, own 2x2 block)
+  const int tid = threadIdx.x;
+  const int npr = (cx.m >> 1) - OFF;
   if (tid < npr) {
     const int p = 2 * tid + OFF;
-    T* pp = M + Sh::addr(p, p);
+    T* pp = cx.M + Sh::addr(p, p);
     T* pq = pp + o01;
     T* qq = pp + o11;
     const T mpp = *pp, mqq = *qq, a = *pq;
@@ -105,13 +100,26 @@ __device__ __forceinline__ void cta_step(T* __restrict__ M, T* __restrict__ cs, 
     *pp = npp;
     *qq = nqq;
     T2 w; w.x = c; w.y = s;
-    cs2[tid] = w;
-    cc[tid] = c;
-    ss[tid] = s;
+    reinterpret_cast<T2*>(cx.cs + OFF * 2 * Sh::kPairsMax)[tid] = w;
+    cx.cc[OFF * Sh::kPairsMax + tid] = c;
+    cx.ss[OFF * Sh::kPairsMax + tid] = s;
   }
-  __syncthreads();
+}
 
-  // ---- phase 2a: 2x2 blocks, B <- G_K B G_L^T (ApplyRot :350-390, positions exchanged)
+// ---- phase 2a: 2x2 blocks, B <- G_K B G_L^T (ApplyRot :350-390, positions exchanged), and in
+// pattern B the strips of the two unpaired end positions
+template <typename T, int NPB, int OFF>
+__device__ __forceinline__ void cta_blocks(const CtaCtx<T>& cx) {
+  using Sh = CtaShape<NPB>;
+  constexpr int o01 = (OFF == 0) ? Sh::kH : 1 - Sh::kH;
+  constexpr int o10 = Sh::kLd;
+  constexpr int o11 = Sh::kLd + o01;
+  const int tid = threadIdx.x;
+  const int npr = (cx.m >> 1) - OFF;
+  T* M = cx.M;
+  const T* cc = cx.cc + OFF * Sh::kPairsMax;
+  const T* ss = cx.ss + OFF * Sh::kPairsMax;
+  const unsigned* tbl = OFF == 0 ? cx.tblA : cx.tblB;
 #pragma unroll
   for (int it = 0; it < Sh::kIt; ++it) {
     const unsigned ent = tbl[it * Sh::kThreads + tid];
@@ -128,11 +136,10 @@ __device__ __forceinline__ void cta_step(T* __restrict__ M, T* __restrict__ cs, 
       b[o11] = jfma(cl, u10, -(sl * u11));
     }
   }
-  // ---- pattern B: row 0 x column pairs, row pairs x column m-1
   if (OFF == 1 && tid < NPB) {
     const int j = tid < NPB / 2 ? tid : tid - NPB / 2;
     if (j < npr) {
-      T* x0 = (tid < NPB / 2) ? M + Sh::addr(0, 2 * j + 1) : M + Sh::addr(2 * j + 1, m - 1);
+      T* x0 = (tid < NPB / 2) ? M + Sh::addr(0, 2 * j + 1) : M + Sh::addr(2 * j + 1, cx.m - 1);
       T* x1 = (tid < NPB / 2) ? x0 + o01 : x0 + o10;
       const T c = cc[j], s = ss[j];
       const T v0 = *x0, v1 = *x1;
@@ -140,33 +147,66 @@ __device__ __forceinline__ void cta_step(T* __restrict__ M, T* __restrict__ cs, 
       *x1 = jfma(c, v0, -(s * v1));
     }
   }
-  // ---- phase 2b: eigenvector rows (ApplyRotLeft :414-418), registers
-  if (EVECS) {
-    const int j0 = 16 * ch;   // pair index of this chunk's first local pair
-    T new_lo = e[0], new_hi = e[31];
-    if (OFF == 1) {
-      // pairs that cross the chunk boundary: (32ch-1, 32ch) = pair j0-1, (32ch+31, 32ch+32) = pair j0+15
-      if (ch > 0 && j0 - 1 < npr) {
-        const T2 r = cs2[j0 - 1];
-        new_lo = jfma(r.x, xhi[(ch - 1) * NPB + v], -(r.y * e[0]));
-      }
-      if (ch < Sh::kChunks - 1 && j0 + 15 < npr) {
-        const T2 r = cs2[j0 + 15];
-        new_hi = jfma(r.y, e[31], r.x * xlo[(ch + 1) * NPB + v]);
-      }
+}
+
+// ---- phase 2b: eigenvector rows (ApplyRotLeft :414-418) of a step of pattern OFF; registers,
+// (c,s) of that step, and for pattern B the two rows received from the neighbouring chunks
+template <typename T, int NPB, int OFF>
+__device__ __forceinline__ void cta_evecs(const CtaCtx<T>& cx, T (&e)[32]) {
+  using Sh = CtaShape<NPB>;
+  using T2 = typename Pair2<T>::type;
+  const int npr = (cx.m >> 1) - OFF;
+  const int ch = cx.ch, v = cx.v;
+  const T2* cs2 = reinterpret_cast<const T2*>(cx.cs + OFF * 2 * Sh::kPairsMax);
+  const int j0 = 16 * ch;   // pair index of this chunk's first local pair
+  T new_lo = e[0], new_hi = e[31];
+  if (OFF == 1) {
+    // pairs that cross the chunk boundary: (32ch-1, 32ch) = pair j0-1, (32ch+31, 32ch+32) = pair j0+15
+    if (ch > 0 && j0 - 1 < npr) {
+      const T2 r = cs2[j0 - 1];
+      new_lo = jfma(r.x, cx.xhi[(ch - 1) * NPB + v], -(r.y * e[0]));
     }
-#pragma unroll
-    for (int jj = 0; jj < 16 - OFF; ++jj) {
-      const int p = 2 * jj + OFF, q = p + 1;
-      if (j0 + jj < npr) {
-        const T2 r = cs2[j0 + jj];
-        const T x = e[p], y = e[q];
-        e[p] = jfma(r.y, x, r.x * y);
-        e[q] = jfma(r.x, x, -(r.y * y));
-      }
+    if (ch < Sh::kChunks - 1 && j0 + 15 < npr) {
+      const T2 r = cs2[j0 + 15];
+      new_hi = jfma(r.y, e[31], r.x * cx.xlo[(ch + 1) * NPB + v]);
     }
-    if (OFF == 1) { e[0] = new_lo; e[31] = new_hi; }
   }
+#pragma unroll
+  for (int jj = 0; jj < 16 - OFF; ++jj) {
+    const int p = 2 * jj + OFF, q = p + 1;
+    if (j0 + jj < npr) {
+      const T2 r = cs2[j0 + jj];
+      const T x = e[p], y = e[q];
+      e[p] = jfma(r.y, x, r.x * y);
+      e[q] = jfma(r.x, x, -(r.y * y));
+    }
+  }
+  if (OFF == 1) { e[0] = new_lo; e[31] = new_hi; }
+}
+
+// One A step + one B step.  Phase 1 occupies npr <= 64 threads while the block waits, so the
+// eigenvector phase of a step is deferred to the next step and runs beside its phase 1:
+//   A: pivot_A, E(previous B) | barrier | blocks_A | barrier
+//   B: pivot_B, E(this A), publish the chunk-boundary rows | barrier | blocks_B | barrier
+// ((c,s) double-buffered by pattern: E reads the other pattern's buffer than pivot writes.)
+template <typename T, int NPB, bool EVECS>
+__device__ __forceinline__ void cta_step_pair(const CtaCtx<T>& cx, T (&e)[EVECS ? 32 : 1], bool have_prev,
+                                              int& n_rot) {
+  using Sh = CtaShape<NPB>;
+  cta_pivot<T, NPB, 0>(cx, n_rot);
+  if constexpr (EVECS) { if (have_prev) cta_evecs<T, NPB, 1>(cx, e); }
+  __syncthreads();
+  cta_blocks<T, NPB, 0>(cx);
+  __syncthreads();
+
+  cta_pivot<T, NPB, 1>(cx, n_rot);
+  if constexpr (EVECS) {
+    cta_evecs<T, NPB, 0>(cx, e);
+    if (cx.ch > 0) cx.xlo[cx.ch * NPB + cx.v] = e[0];
+    if (cx.ch < Sh::kChunks - 1) cx.xhi[cx.ch * NPB + cx.v] = e[31];
+  }
+  __syncthreads();
+  cta_blocks<T, NPB, 1>(cx);
   __syncthreads();
 }
 
@@ -188,13 +228,16 @@ jpd_cta_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict__
 
   T* M = reinterpret_cast<T*>(smem_raw + Sh::table_bytes());
   T* cs = M + Sh::kMElems;
-  T* cc = cs + 2 * Sh::kPairsMax;
-  T* ss = cc + Sh::kPairsMax;
-  T* ev = ss + Sh::kPairsMax;
+  T* cc = cs + 2 * 2 * Sh::kPairsMax;
+  T* ss = cc + 2 * Sh::kPairsMax;
+  T* ev = ss + 2 * Sh::kPairsMax;
   T* xlo = ev + NPB;
   T* xhi = xlo + Sh::kChunks * NPB;
   int* perm = reinterpret_cast<int*>(smem_raw + Sh::table_bytes() + ((size_t)Sh::kElems * sizeof(T) + 15) / 16 * 16);
   int* rot_total = perm + NPB;
+  CtaCtx<T> cx;
+  cx.M = M; cx.cs = cs; cx.cc = cc; cx.ss = ss; cx.xlo = xlo; cx.xhi = xhi;
+  cx.tblA = tblA; cx.tblB = tblB; cx.m = m; cx.v = v; cx.ch = ch;
   __syncthreads();
 
   for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
@@ -232,10 +275,8 @@ jpd_cta_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict__
       }
       need = __syncthreads_or(mine) != 0;
       if (!need || sweeps >= max_num_sweeps) break;
-      for (int step = 0; step < m; step += 2) {
-        cta_step<T, NPB, EVECS, 0>(M, cs, cc, ss, xlo, xhi, tblA, e, m, v, ch, n_rot);
-        cta_step<T, NPB, EVECS, 1>(M, cs, cc, ss, xlo, xhi, tblB, e, m, v, ch, n_rot);
-      }
+      for (int step = 0; step < m; step += 2) cta_step_pair<T, NPB, EVECS>(cx, e, step > 0, n_rot);
+      if constexpr (EVECS) cta_evecs<T, NPB, 1>(cx, e);   // the last B step's eigenvector phase
       ++sweeps;
     }
     // max_num_sweeps == 0: the reference reports failure for n > 1 whatever the matrix (:185-186, :214-219)
