@@ -174,15 +174,15 @@ def fp_peak(jpd, torch, elem=8):
 
 def side_workloads(jpd, torch, hbm_peak):
     """The other sizes the metric and the configs name (n=3 thread tier, n=16/32 warp tier,
-    n=128 CTA tier; fp64), device-resident, one GPU: context lines inside the JSON, not the
-    headline."""
+    n=128 CTA tier, n=256 cluster tier; fp64), device-resident, one GPU: context lines inside
+    the JSON, not the headline."""
     out = {}
     fp64_tflops = fp_peak(jpd, torch, 8)
     out["fp64_fma_peak_tflops_measured"] = round(fp64_tflops, 2)
     # mean rotations of the reference on these inputs (r_ref, SURVEY 8(d)) -> flop roofline
-    r_ref = {3: 8.71, 16: 486.0, 32: 2078.0, 128: 35388.8}
+    r_ref = {3: 8.71, 16: 486.0, 32: 2078.0, 128: 35388.8, 256: 143937.8}
     cases = ((3, 1 << 23, jpd.LAYOUT_SOA, 5), (16, 1 << 18, jpd.LAYOUT_AOS, 5),
-             (32, 1 << 17, jpd.LAYOUT_AOS, 5), (128, 2048, jpd.LAYOUT_AOS, 2))
+             (32, 1 << 17, jpd.LAYOUT_AOS, 5), (128, 2048, jpd.LAYOUT_AOS, 2), (256, 528, jpd.LAYOUT_AOS, 1))
     for n, batch, layout, reps in cases:
         shape = (n, n, batch) if layout == jpd.LAYOUT_SOA else (batch, n, n)
         m = torch.empty(shape, dtype=torch.float64, device="cuda")
