@@ -130,6 +130,29 @@ class ClockSampler:
                 "power_w_max": max(s[2] for s in used), "reasons": reasons}
 
 
+def _bind_to_gpu_numa_node(cuda_index):
+    """Run this rank on the CPUs next to its GPU (NVML's affinity mask) BEFORE the pinned host
+    buffers of the e2e arm are allocated, so that they land on the GPU's NUMA node and the
+    PCIe copies do not cross the socket interconnect.  Best effort: silently skipped when NVML
+    cannot tell."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+    except Exception:
+        pass
+
+
 def time_device_steps(fn, steps, warmup, barrier, sampler=None):
     """W warm-up steps, then exactly K steps between barrier+synchronize; returns ms total."""
     import torch
@@ -280,6 +303,7 @@ def run_own_arm(args):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path "
                          "(use --impl reference for the CPU reference arm)")
     torch.cuda.set_device(local_rank)
+    _bind_to_gpu_numa_node(local_rank)
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
