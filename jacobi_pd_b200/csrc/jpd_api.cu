@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -364,7 +365,13 @@ int diagonalize_host(const T* h_mat, T* h_evals, T* h_evecs, int* h_iters, int n
 
   const size_t nn = (size_t)n * n;
   const size_t per_matrix = sizeof(T) * (nn + n + (calc ? nn : 0)) + 4;
-  long long chunk = std::max<long long>(1, (long long)((size_t)64 << 20) / (long long)per_matrix);
+  // bytes per pipeline chunk (in + out): 64 MB by default, JPD_HOST_CHUNK_MB overrides (tuning aid)
+  size_t chunk_bytes = (size_t)64 << 20;
+  if (const char* env = std::getenv("JPD_HOST_CHUNK_MB")) {
+    const long mb = std::strtol(env, nullptr, 10);
+    if (mb >= 1 && mb <= 4096) chunk_bytes = (size_t)mb << 20;
+  }
+  long long chunk = std::max<long long>(1, (long long)chunk_bytes / (long long)per_matrix);
   chunk = std::min(chunk, batch);
   if (layout == JPD_LAYOUT_SOA && chunk > 1) chunk &= ~1LL;  // keep planes 16-byte aligned
 
