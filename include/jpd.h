@@ -20,8 +20,8 @@
  *     ties resolve as the reference's selection sort does   (jacobi_pd.hpp:56-62, 477-508)
  *   - n_iters[b] > 0  : converged (rotations performed + 1)
  *     n_iters[b] == 0 : max_num_sweeps exhausted and n > 1   (jacobi_pd.hpp:214-219)
- * Deliberate deviations (DESIGN.md "deviations"): pair order is a static round-robin, not
- * max-pivot, so rotation counts and the DO_NOT_SORT order differ for n > 2; when
+ * Deliberate deviations (DESIGN.md "deviations"): pair order is static (round-robin / odd-even
+ * parallel ordering), not max-pivot, so rotation counts and the DO_NOT_SORT order differ for n > 2; when
  * calc_evecs == 0 the evecs buffer may be NULL and is never touched.
  *
  * Layouts (argument `layout`):

@@ -1,4 +1,6 @@
-// jpd_block.cuh -- tier 2/3: one thread block per matrix, parallel-ordering sweeps.
+// jpd_block.cuh -- tier 5 (n > 256; the first-generation kernel, which ran n = 7..256 until
+// jpd_warp.cuh / jpd_cta.cuh / jpd_cluster.cuh replaced it there): one thread block per matrix,
+// round-robin parallel-ordering sweeps.
 //
 // Path being replaced: Jacobi::Diagonalize, /root/reference/include/jacobi_pd.hpp:159-220.
 // The reference applies ONE max-pivot rotation at a time (MaxEntry :444-468); a block
@@ -14,8 +16,8 @@
 //             pair any two indices.  Eigenvector rows p_k,q_k get R_k^T (:414-418).
 //
 // Storage: M (n x ldm, ldm odd => conflict-free column access) and E (n x n) live in
-// shared memory when they fit (tier 2), otherwise in a per-block global workspace that
-// stays L2 resident (tier 3).  Convergence: a full sweep in which no pair needed a
+// shared memory when they fit, otherwise (always, at the sizes that still reach this kernel)
+// in a per-block global workspace that stays L2 resident.  Convergence: a full sweep in which no pair needed a
 // rotation (block vote through __syncthreads_or).  Return value as the reference:
 // rotations + 1, or 0 when max_num_sweeps sweeps were not enough (:214-219).
 #pragma once
