@@ -1,0 +1,36 @@
+# dev tool: randomized parity soak -- many sizes x seeds x sort criteria x dtypes against the oracle
+import sys, time; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+import numpy as np
+from oracle import binding as ob
+import parity
+from gpu_util import run_gpu
+rng = np.random.default_rng(2026)
+t0 = time.time(); cases = 0; worst = {}
+sizes = list(range(1, 41)) + [45, 48, 50, 63, 64, 65, 80, 96, 97, 100, 127, 128, 129, 150, 192, 200, 255, 256]
+for rep in range(3):
+    for n in sizes:
+        B = 64 if n <= 8 else (24 if n <= 40 else (6 if n <= 128 else 3))
+        for dtype in (np.float64, np.float32):
+            kind = rng.integers(0, 3)
+            if kind == 0:
+                A = rng.uniform(-1, 1, (B, n, n))
+            elif kind == 1:
+                A = rng.normal(size=(B, n, n)) * 10.0 ** rng.uniform(-6, 6, (B, 1, 1))
+            else:
+                q, _ = np.linalg.qr(rng.normal(size=(B, n, n)))
+                lam = np.round(rng.uniform(-3, 3, (B, n)))            # heavy exact degeneracy
+                A = np.einsum("bki,bk,bkj->bij", q, lam, q)
+            A = np.ascontiguousarray((np.triu(A) + np.triu(A, 1).swapaxes(1, 2)).astype(dtype))
+            sort = int(rng.integers(0, 5)); layout = int(rng.integers(0, 2))
+            ref = ob.oracle_diagonalize(A, sort)
+            out = run_gpu(A, sort, layout=layout)
+            if kind == 2 and sort in (3, 4):     # |key| ties: order of +-l not defined
+                parity.check_evals(np.abs(out[0]), np.abs(ref[0])); parity.check_residual_orth(A, out[0], out[1]); parity.check_iters(out[2], ref[2])
+                st = {}
+            else:
+                st = parity.full_check(A, out, ref, sort, compare_vectors=(kind != 2))
+            for k, v in st.items():
+                if k in ("eval_err", "res", "orth"):
+                    key = (k, np.dtype(dtype).name); worst[key] = max(worst.get(key, 0), v)
+            cases += 1
+print("soak ok:", cases, "cases in", round(time.time() - t0, 1), "s; worst:", {k: float(f"{v:.3g}") for k, v in worst.items()})
