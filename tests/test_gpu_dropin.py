@@ -53,3 +53,12 @@ def test_cpp_batched_front_end():
         pytest.skip("tests/dropin/test_batched_frontend not built")
     res = subprocess.run([path], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "test passed" in res.stdout, res.stdout + res.stderr
+
+
+def test_cpp_device_front_end_and_fused_producers():
+    """CUDA C++ caller of BatchedJacobi::Diagonalize / QuaternionFromCorrelation / PrincipalAxes."""
+    path = os.path.join(ROOT, "tests", "dropin", "test_device_frontend")
+    if not os.path.exists(path):
+        pytest.skip("tests/dropin/test_device_frontend not built")
+    res = subprocess.run([path], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "test passed" in res.stdout, res.stdout + res.stderr
