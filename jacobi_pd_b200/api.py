@@ -86,7 +86,7 @@ def diagonalize_batched(mat, n: int | None = None, layout: int = LAYOUT_AOS,
 
 
 def quaternion_from_correlation(corr, layout: int = LAYOUT_AOS, all_eigenpairs: bool = False,
-                                max_num_sweeps: int = 50, stream=None):
+                                max_num_sweeps: int = 50, stream=None, out=None):
     """colvars optimal-rotation path fused in one kernel: 3x3 correlation matrices (CUDA
     tensor, AoS ``(batch, 9)``/``(batch, 3, 3)`` or SoA ``(9, batch)``) -> ``(lambda, quat,
     n_iters)``; with ``all_eigenpairs`` the four eigenvalues (decreasing) and the 4x4
@@ -102,9 +102,12 @@ def quaternion_from_correlation(corr, layout: int = LAYOUT_AOS, all_eigenpairs: 
         es, vs = out_shapes(4, batch, layout)
     else:
         es, vs = ((batch,), (batch, 4)) if layout == LAYOUT_AOS else ((batch,), (4, batch))
-    lam = torch.empty(es, dtype=corr.dtype, device=corr.device)
-    quat = torch.empty(vs, dtype=corr.dtype, device=corr.device)
-    iters = torch.empty((batch,), dtype=torch.int32, device=corr.device)
+    if out is None:
+        lam = torch.empty(es, dtype=corr.dtype, device=corr.device)
+        quat = torch.empty(vs, dtype=corr.dtype, device=corr.device)
+        iters = torch.empty((batch,), dtype=torch.int32, device=corr.device)
+    else:                                   # reuse the caller's (lambda, quat, n_iters) buffers
+        lam, quat, iters = out
     st = torch.cuda.current_stream(corr.device).cuda_stream if stream is None else stream
     with torch.cuda.device(corr.device):
         rc = getattr(_lib.lib(), f"jpd_quaternion_from_correlation_{sfx}")(
@@ -114,7 +117,7 @@ def quaternion_from_correlation(corr, layout: int = LAYOUT_AOS, all_eigenpairs: 
     return lam, quat, iters
 
 
-def principal_axes(inertia6, layout: int = LAYOUT_AOS, max_num_sweeps: int = 50, stream=None):
+def principal_axes(inertia6, layout: int = LAYOUT_AOS, max_num_sweeps: int = 50, stream=None, out=None):
     """LAMMPS rigid-body path fused in one kernel: (Ixx, Iyy, Izz, Iyz, Ixz, Ixy) per body
     (CUDA tensor, AoS ``(batch, 6)`` or SoA ``(6, batch)``) -> ``(moments, axes, n_iters)``:
     moments decreasing, ``axes[b, i, k]`` = component i of principal axis k, right-handed."""
@@ -126,9 +129,12 @@ def principal_axes(inertia6, layout: int = LAYOUT_AOS, max_num_sweeps: int = 50,
         raise ValueError("inertia6 must hold 6 scalars per body")
     sfx = _suffix(inertia6.dtype)
     es, vs = out_shapes(3, batch, layout)
-    mom = torch.empty(es, dtype=inertia6.dtype, device=inertia6.device)
-    axes = torch.empty(vs, dtype=inertia6.dtype, device=inertia6.device)
-    iters = torch.empty((batch,), dtype=torch.int32, device=inertia6.device)
+    if out is None:
+        mom = torch.empty(es, dtype=inertia6.dtype, device=inertia6.device)
+        axes = torch.empty(vs, dtype=inertia6.dtype, device=inertia6.device)
+        iters = torch.empty((batch,), dtype=torch.int32, device=inertia6.device)
+    else:
+        mom, axes, iters = out
     st = torch.cuda.current_stream(inertia6.device).cuda_stream if stream is None else stream
     with torch.cuda.device(inertia6.device):
         rc = getattr(_lib.lib(), f"jpd_principal_axes_{sfx}")(
