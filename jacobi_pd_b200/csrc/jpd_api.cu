@@ -11,6 +11,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -337,7 +338,11 @@ struct Slot {
 struct Pipeline {
   std::mutex mutex;
   Slot slot[3];
+  // small-call path (batch = 1 through the drop-in class): one pinned + one device buffer
+  void* small_pin = nullptr;
+  void* small_dev = nullptr;
 };
+constexpr size_t kSmallCallBytes = (size_t)1 << 20;
 Pipeline g_pipe[kMaxDevices];
 
 int grow(void** p, size_t* have, size_t want) {
@@ -365,6 +370,39 @@ int diagonalize_host(const T* h_mat, T* h_evals, T* h_evecs, int* h_iters, int n
 
   const size_t nn = (size_t)n * n;
   const size_t per_matrix = sizeof(T) * (nn + n + (calc ? nn : 0)) + 4;
+
+  // ---- small calls (the drop-in scalar class: batch = 1): everything through ONE pinned
+  // staging buffer -- one H2D copy, the kernel, one D2H copy of evals|evecs|n_iters, one
+  // synchronisation -- instead of the chunked three-stream pipeline (5 copies, 3 syncs)
+  {
+    auto up16 = [](size_t x) { return (x + 15) / 16 * 16; };
+    const size_t in_b = sizeof(T) * nn * batch, ev_b = sizeof(T) * n * batch;
+    const size_t vec_b = calc ? sizeof(T) * nn * batch : 0, it_b = sizeof(int) * batch;
+    const size_t ev_off = up16(in_b), vec_off = ev_off + up16(ev_b), it_off = vec_off + up16(vec_b);
+    const size_t total = it_off + it_b;
+    if (total <= kSmallCallBytes && host_pitch == batch) {
+      if (!pipe.small_pin) {
+        JPD_CK(cudaHostAlloc(&pipe.small_pin, kSmallCallBytes, cudaHostAllocDefault));
+        JPD_CK(cudaMalloc(&pipe.small_dev, kSmallCallBytes));
+      }
+      if (!pipe.slot[0].stream) JPD_CK(cudaStreamCreateWithFlags(&pipe.slot[0].stream, cudaStreamNonBlocking));
+      cudaStream_t st = pipe.slot[0].stream;
+      char* hp = static_cast<char*>(pipe.small_pin);
+      char* dp = static_cast<char*>(pipe.small_dev);
+      std::memcpy(hp, h_mat, in_b);
+      JPD_CK(cudaMemcpyAsync(dp, hp, in_b, cudaMemcpyHostToDevice, st));
+      const int rc = diagonalize_device<T>(reinterpret_cast<const T*>(dp), reinterpret_cast<T*>(dp + ev_off),
+                                           calc ? reinterpret_cast<T*>(dp + vec_off) : nullptr,
+                                           reinterpret_cast<int*>(dp + it_off), n, batch, layout, sort, calc, sweeps, st);
+      if (rc != JPD_OK) return rc;
+      JPD_CK(cudaMemcpyAsync(hp + ev_off, dp + ev_off, total - ev_off, cudaMemcpyDeviceToHost, st));
+      JPD_CK(cudaStreamSynchronize(st));
+      std::memcpy(h_evals, hp + ev_off, ev_b);
+      if (calc) std::memcpy(h_evecs, hp + vec_off, vec_b);
+      if (h_iters) std::memcpy(h_iters, hp + it_off, it_b);
+      return JPD_OK;
+    }
+  }
   // bytes per pipeline chunk (in + out): 64 MB by default, JPD_HOST_CHUNK_MB overrides (tuning aid)
   size_t chunk_bytes = (size_t)64 << 20;
   if (const char* env = std::getenv("JPD_HOST_CHUNK_MB")) {
@@ -673,8 +711,11 @@ int jpd_release(void) {
     std::lock_guard<std::mutex> lock(pipe.mutex);
     bool any = false;
     for (auto& sl : pipe.slot) any = any || sl.stream || sl.in || sl.evals || sl.evecs || sl.iters;
+    any = any || pipe.small_pin || pipe.small_dev;
     if (!any) continue;
     cudaSetDevice(d);
+    if (pipe.small_pin) { cudaFreeHost(pipe.small_pin); pipe.small_pin = nullptr; }
+    if (pipe.small_dev) { cudaFree(pipe.small_dev); pipe.small_dev = nullptr; }
     for (auto& sl : pipe.slot) {
       if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
       cudaFree(sl.in); cudaFree(sl.evals); cudaFree(sl.evecs); cudaFree(sl.iters);
