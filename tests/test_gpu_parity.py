@@ -99,3 +99,33 @@ def test_synthetic_generator_bits_match_host_twin():
             jpd.fill_synthetic(d, n, B, layout, kind, 4321, b0=5)
             h = ob.fill_synthetic(n, B, layout, kind, 4321, b0=5, dtype=dt)
             assert np.array_equal(d.cpu().numpy(), h)
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+def test_multi_gpu_host_entry_slices_without_changing_results(layout):
+    """jpd_diagonalize_batched_host_multi_*: the batch is cut into contiguous slices, one per
+    device (all visible devices, at most 4); results must be bit-identical to the
+    single-device call (independent units, no collective)."""
+    import torch
+    import jacobi_pd_b200 as jpd
+    n_dev = max(1, min(4, torch.cuda.device_count()))
+    for n, B in ((4, 10007), (12, 1001), (40, 67)):
+        A = ob.fill_synthetic(n, B, seed=500 + n)
+        src = np.ascontiguousarray(A if layout == 0 else A.transpose(1, 2, 0))
+        es, vs = jpd.api.out_shapes(n, B, layout)
+        outs = []
+        for devices in (1, n_dev):
+            ev, vec, it = np.empty(es), np.empty(vs), np.empty(B, np.int32)
+            jpd.diagonalize_batched_host(src, ev, vec, it, n, B, layout, 1, True, 50, n_devices=devices) if devices > 1 else \
+                jpd.diagonalize_batched_host(src, ev, vec, it, n, B, layout, 1, True, 50)
+            outs.append((ev, vec, it))
+        # also the multi entry with a single device
+        ev, vec, it = np.empty(es), np.empty(vs), np.empty(B, np.int32)
+        l = jpd.lib()
+        rc = l.jpd_diagonalize_batched_host_multi_f64(src.ctypes.data, ev.ctypes.data, vec.ctypes.data, it.ctypes.data,
+                                                      n, B, layout, 1, 1, 50, 1, None)
+        assert rc == 0
+        outs.append((ev, vec, it))
+        for o in outs[1:]:
+            for x, y in zip(outs[0], o):
+                assert np.array_equal(x, y)
