@@ -200,16 +200,8 @@ __device__ __forceinline__ bool cluster_pivot(const ClusterCtx<T>& cx, int buf, 
     }
     __syncwarp();                         // every quad has read its old entries
     if (act) {
-      T c = T(1), s = T(0), npp = mqq, nqq = mpp;
-      const bool rot = pair_needs_rotation(a, mpp, mqq);
-      if (rot) {
-        const T d = mqq - mpp;
-        T t;
-        jacobi_rotation(d, a, rotation_range_unsafe(d, a), c, s, t);
-        const T gg = t * a;
-        npp = mqq + gg;
-        nqq = mpp - gg;
-      }
+      T c, s, npp, nqq;
+      const bool rot = pivot_exchange_rotation(mpp, mqq, a, c, s, npp, nqq);
       st_cluster(cluster_map(cc_u + (unsigned)(j * esz), target), c);
       st_cluster(cluster_map(ss_u + (unsigned)(j * esz), target), s);
       wrote_remote = true;
@@ -244,19 +236,17 @@ __device__ __forceinline__ bool cluster_blocks(const ClusterCtx<T>& cx, int buf)
       const int K = (ent.x >> 16) & 0x7fu, L = (ent.x >> 23) & 0x7fu;
       const bool remote = (OFF == 1) && ((ent.x >> 30) & 1u);   // pattern A pairs never leave their CTA
       const T ck = cc[K], sk = ss[K], cl = cc[L], sl = ss[L];
-      const T b00 = b[0], b01 = b[o01];
+      T b00 = b[0], b01 = b[o01];
       T b10, b11;
       T* b1 = M + ent.y;
       const unsigned a10 = ent.y, a11 = ent.y + (unsigned)(o01 * esz);
       if (remote) { b10 = ld_cluster(a10, T(0)); b11 = ld_cluster(a11, T(0)); }
       else { b10 = b1[0]; b11 = b1[o01]; }
-      const T u00 = jfma(sk, b00, ck * b10), u01 = jfma(sk, b01, ck * b11);
-      const T u10 = jfma(ck, b00, -(sk * b10)), u11 = jfma(ck, b01, -(sk * b11));
-      b[0] = jfma(sl, u00, cl * u01);
-      b[o01] = jfma(cl, u00, -(sl * u01));
-      const T n10 = jfma(sl, u10, cl * u11), n11 = jfma(cl, u10, -(sl * u11));
-      if (remote) { st_cluster(a10, n10); st_cluster(a11, n11); wrote_remote = true; }
-      else { b1[0] = n10; b1[o01] = n11; }
+      exchange_rotate_block(b00, b01, b10, b11, ck, sk, cl, sl);
+      b[0] = b00;
+      b[o01] = b01;
+      if (remote) { st_cluster(a10, b10); st_cluster(a11, b11); wrote_remote = true; }
+      else { b1[0] = b10; b1[o01] = b11; }
     }
   }
   // pattern B: row 0 x column pairs (CTA owning row 0), row pairs x column m-1
@@ -265,19 +255,18 @@ __device__ __forceinline__ bool cluster_blocks(const ClusterCtx<T>& cx, int buf)
       const int j = tid - 64;
       if (j < npr) {
         T* x0 = M + Sh::lrow(0) * Sh::kLd + Sh::slot(2 * j + 1);
-        const T c = cc[j], s = ss[j];
-        const T v0 = x0[0], v1 = x0[o01];
-        x0[0] = jfma(s, v0, c * v1);
-        x0[o01] = jfma(c, v0, -(s * v1));
+        T v0 = x0[0], v1 = x0[o01];
+        exchange_rotate_pair(v0, v1, cc[j], ss[j]);
+        x0[0] = v0; x0[o01] = v1;
       }
     } else if (tid >= 32 && tid < 64) {
       const int j = cl_pair_of(tid - 32, cx.rank);
       if (j < npr) {
         const unsigned a0 = cl_eaddr<T>(cx.sp.m, 2 * j + 1, cx.m - 1), a1 = cl_eaddr<T>(cx.sp.m, 2 * j + 2, cx.m - 1);
-        const T c = cc[j], s = ss[j];
-        const T v0 = ld_cluster(a0, T(0)), v1 = ld_cluster(a1, T(0));
-        st_cluster(a0, jfma(s, v0, c * v1));
-        st_cluster(a1, jfma(c, v0, -(s * v1)));
+        T v0 = ld_cluster(a0, T(0)), v1 = ld_cluster(a1, T(0));
+        exchange_rotate_pair(v0, v1, cc[j], ss[j]);
+        st_cluster(a0, v0);
+        st_cluster(a1, v1);
         wrote_remote = true;
       }
     }
@@ -310,10 +299,7 @@ __device__ __forceinline__ void cluster_evecs(const ClusterCtx<T>& cx, int buf, 
   for (int jj = 0; jj < 16 - OFF; ++jj) {
     const int p = 2 * jj + OFF, q = p + 1;
     if (j0 + jj < npr) {
-      const T rc = cc[j0 + jj], rs = ss[j0 + jj];
-      const T x = e[p], y = e[q];
-      e[p] = jfma(rs, x, rc * y);
-      e[q] = jfma(rc, x, -(rs * y));
+      exchange_rotate_pair(e[p], e[q], cc[j0 + jj], ss[j0 + jj]);
     }
   }
   if (OFF == 1) { e[0] = new_lo; e[31] = new_hi; }

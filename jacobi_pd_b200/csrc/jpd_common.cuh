@@ -279,4 +279,44 @@ JPD_HD void jacobi_rotation(T d, T a, bool any_unsafe, T& c, T& s, T& t) {
   rotation_from_scaled(d, a, d_is_zero, d_neg, c, s, t);
 }
 
+// ---- shared by the parallel-ordering tiers (jpd_warp.cuh, jpd_cta.cuh, jpd_cluster.cuh) ----
+// The "rotation" of those tiers also exchanges the two positions of its pair (odd-even
+// ordering): applied to a 2-vector it is G = [[s, c], [c, -s]].
+
+// Pivot pair with diagonal entries (mpp, mqq) and off-diagonal entry a: skip test
+// (jacobi_pd.hpp:191), CalcRot (:233-256), new diagonal entries (:337-338) at the EXCHANGED
+// positions.  Returns whether a rotation was needed; otherwise (c,s) = (1,0): a pure exchange.
+template <typename T>
+JPD_HD bool pivot_exchange_rotation(T mpp, T mqq, T a, T& c, T& s, T& npp, T& nqq) {
+  c = T(1); s = T(0); npp = mqq; nqq = mpp;
+  if (!pair_needs_rotation(a, mpp, mqq)) return false;
+  const T d = mqq - mpp;
+  T t;
+  jacobi_rotation(d, a, rotation_range_unsafe(d, a), c, s, t);
+  const T g = t * a;
+  npp = mqq + g;
+  nqq = mpp - g;
+  return true;
+}
+
+// 2x2 block B = [[b00, b01], [b10, b11]] (rows: pair K, columns: pair L)  <-  G_K B G_L^T
+// (ApplyRot :350-390 for both rotations at once): 8 multiplications + 8 FMAs.
+template <typename T>
+JPD_HD void exchange_rotate_block(T& b00, T& b01, T& b10, T& b11, T ck, T sk, T cl, T sl) {
+  const T u00 = jfma(sk, b00, ck * b10), u01 = jfma(sk, b01, ck * b11);
+  const T u10 = jfma(ck, b00, -(sk * b10)), u11 = jfma(ck, b01, -(sk * b11));
+  b00 = jfma(sl, u00, cl * u01);
+  b01 = jfma(cl, u00, -(sl * u01));
+  b10 = jfma(sl, u10, cl * u11);
+  b11 = jfma(cl, u10, -(sl * u11));
+}
+
+// 2-vector (x, y)  <-  G (x, y): rows of E (ApplyRotLeft :414-418), end strips of pattern B
+template <typename T>
+JPD_HD void exchange_rotate_pair(T& x, T& y, T c, T s) {
+  const T nx = jfma(s, x, c * y);
+  y = jfma(c, x, -(s * y));
+  x = nx;
+}
+
 }  // namespace jpd

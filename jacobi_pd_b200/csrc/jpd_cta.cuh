@@ -86,14 +86,8 @@ __device__ __forceinline__ void cta_pivot(const CtaCtx<T>& cx, int& n_rot) {
     T* pq = pp + o01;
     T* qq = pp + o11;
     const T mpp = *pp, mqq = *qq, a = *pq;
-    T c = T(1), s = T(0), npp = mqq, nqq = mpp;
-    if (pair_needs_rotation(a, mpp, mqq)) {
-      const T d = mqq - mpp;
-      T t;
-      jacobi_rotation(d, a, rotation_range_unsafe(d, a), c, s, t);
-      const T g = t * a;
-      npp = mqq + g;
-      nqq = mpp - g;
+    T c, s, npp, nqq;
+    if (pivot_exchange_rotation(mpp, mqq, a, c, s, npp, nqq)) {
       *pq = T(0);
       ++n_rot;
     }
@@ -127,13 +121,9 @@ __device__ __forceinline__ void cta_blocks(const CtaCtx<T>& cx) {
       T* b = M + (ent & 0xffffu);
       const int K = (ent >> 16) & 0xffu, L = ent >> 24;
       const T ck = cc[K], sk = ss[K], cl = cc[L], sl = ss[L];
-      const T b00 = b[0], b01 = b[o01], b10 = b[o10], b11 = b[o11];
-      const T u00 = jfma(sk, b00, ck * b10), u01 = jfma(sk, b01, ck * b11);
-      const T u10 = jfma(ck, b00, -(sk * b10)), u11 = jfma(ck, b01, -(sk * b11));
-      b[0] = jfma(sl, u00, cl * u01);
-      b[o01] = jfma(cl, u00, -(sl * u01));
-      b[o10] = jfma(sl, u10, cl * u11);
-      b[o11] = jfma(cl, u10, -(sl * u11));
+      T b00 = b[0], b01 = b[o01], b10 = b[o10], b11 = b[o11];
+      exchange_rotate_block(b00, b01, b10, b11, ck, sk, cl, sl);
+      b[0] = b00; b[o01] = b01; b[o10] = b10; b[o11] = b11;
     }
   }
   if (OFF == 1 && tid < NPB) {
@@ -141,10 +131,9 @@ __device__ __forceinline__ void cta_blocks(const CtaCtx<T>& cx) {
     if (j < npr) {
       T* x0 = (tid < NPB / 2) ? M + Sh::addr(0, 2 * j + 1) : M + Sh::addr(2 * j + 1, cx.m - 1);
       T* x1 = (tid < NPB / 2) ? x0 + o01 : x0 + o10;
-      const T c = cc[j], s = ss[j];
-      const T v0 = *x0, v1 = *x1;
-      *x0 = jfma(s, v0, c * v1);
-      *x1 = jfma(c, v0, -(s * v1));
+      T v0 = *x0, v1 = *x1;
+      exchange_rotate_pair(v0, v1, cc[j], ss[j]);
+      *x0 = v0; *x1 = v1;
     }
   }
 }
@@ -176,9 +165,7 @@ __device__ __forceinline__ void cta_evecs(const CtaCtx<T>& cx, T (&e)[32]) {
     const int p = 2 * jj + OFF, q = p + 1;
     if (j0 + jj < npr) {
       const T2 r = cs2[j0 + jj];
-      const T x = e[p], y = e[q];
-      e[p] = jfma(r.y, x, r.x * y);
-      e[q] = jfma(r.x, x, -(r.y * y));
+      exchange_rotate_pair(e[p], e[q], r.x, r.y);
     }
   }
   if (OFF == 1) { e[0] = new_lo; e[31] = new_hi; }
