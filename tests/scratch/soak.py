@@ -7,7 +7,7 @@ from gpu_util import run_gpu
 rng = np.random.default_rng(2026)
 t0 = time.time(); cases = 0; worst = {}
 sizes = list(range(1, 41)) + [45, 48, 50, 63, 64, 65, 80, 96, 97, 100, 127, 128, 129, 150, 192, 200, 255, 256]
-for rep in range(3):
+for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
     for n in sizes:
         B = 64 if n <= 8 else (24 if n <= 40 else (6 if n <= 128 else 3))
         for dtype in (np.float64, np.float32):
@@ -28,7 +28,15 @@ for rep in range(3):
                 parity.check_evals(np.abs(out[0]), np.abs(ref[0])); parity.check_residual_orth(A, out[0], out[1]); parity.check_iters(out[2], ref[2])
                 st = {}
             else:
-                st = parity.full_check(A, out, ref, sort, compare_vectors=(kind != 2))
+                try:
+                    st = parity.full_check(A, out, ref, sort, compare_vectors=(kind != 2))
+                except AssertionError as ex:
+                    sc = np.abs(ref[0].astype(np.float64)).max(axis=1)
+                    err = np.abs(out[0].astype(np.float64) - ref[0].astype(np.float64)).max(axis=1) / np.where(sc > 0, sc, 1)
+                    b = int(np.nanargmax(err))
+                    print("FAIL", dict(rep=rep, n=n, dtype=np.dtype(dtype).name, kind=int(kind), sort=sort, layout=layout, b=b), str(ex)[:120])
+                    print(" gpu ", out[0][b]); print(" ref ", ref[0][b]); print(" iters gpu/ref", out[2][b], ref[2][b])
+                    raise
             for k, v in st.items():
                 if k in ("eval_err", "res", "orth"):
                     key = (k, np.dtype(dtype).name); worst[key] = max(worst.get(key, 0), v)
