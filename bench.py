@@ -376,11 +376,30 @@ def run_own_arm(args):
             e2e_step()
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
+        # context: the same byte volumes as plain concurrent pinned copies (the PCIe bound of this arm)
+        pcie_bound = None
+        if rank == 0 and world == 1 and not args.no_extras:
+            d_in = torch.empty((eb, n, n), dtype=torch.float64, device="cuda")
+            d_out = torch.empty((eb * (n + n * n) + (eb + 1) // 2,), dtype=torch.float64, device="cuda")
+            h_out = torch.empty(d_out.shape, dtype=torch.float64).pin_memory()
+            s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+            best = 1e30
+            for _ in range(3):
+                torch.cuda.synchronize(); t1 = time.perf_counter()
+                with torch.cuda.stream(s_up):
+                    d_in.copy_(h_mat, non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    h_out.copy_(d_out, non_blocking=True)
+                torch.cuda.synchronize(); best = min(best, time.perf_counter() - t1)
+            pcie_bound = eb / best
+            del d_in, d_out, h_out
         e2e = {"value": eb * world * e2e_steps / dt, "unit": "matrices/s",
                "h2d_bytes_per_step": int(h_mat.numel() * 8),
                "d2h_bytes_per_step": int(h_ev.numel() * 8 + h_vec.numel() * 8 + h_it.numel() * 4),
                "steps": e2e_steps, "batch_per_gpu": eb, "host_layout": "aos", "host_memory": "pinned",
-               "checksum_evals": float(h_ev[:: max(1, eb // 4096)].sum().item())}
+               "checksum_evals": float(h_ev[:: max(1, eb // 4096)].sum().item()),
+               "pcie_copy_bound": pcie_bound,
+               "frac_of_pcie_copy_bound": (eb * e2e_steps / dt / pcie_bound) if pcie_bound else None}
         del h_mat, h_ev, h_vec, h_it
 
     line = None
