@@ -13,7 +13,8 @@
 //    eigenvectors as COLUMNS and a right-handed frame (ez flipped if (ex x ey).ez < 0).
 //
 // Both reuse small_solve() of jpd_small.cuh unchanged: same rotation, same skip test,
-// same sweep logic, same return value.
+// same sweep logic, same return value (the producer is the `load` callback, so that the
+// rare rescaling pass can rebuild the matrix from the inputs).
 #pragma once
 #include "jpd_small.cuh"
 
@@ -40,54 +41,54 @@ jpd_quat_kernel(const T* __restrict__ corr, T* __restrict__ lambda, T* __restric
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = gid < batch;
   const long long b = live ? gid : batch - 1;
-  T R[9];
+  auto load = [&](T (&m)[10]) {
+    T R[9];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) R[k] = SOA ? __ldg(corr + (long long)k * batch + b) : __ldg(corr + b * 9 + k);
-  T m[10], e[16];
-  overlap_from_correlation(R, m);
-  const int iters = small_solve<4, T, true>(m, e, max_num_sweeps);
-  T ev[4];
+    for (int k = 0; k < 9; ++k) R[k] = SOA ? __ldg(corr + (long long)k * batch + b) : __ldg(corr + b * 9 + k);
+    overlap_from_correlation(R, m);
+  };
+  auto emit = [&](const T (&m)[10], const T (&e)[16], int iters) {
+    T ev[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) ev[i] = m[SmallShape<4>::tri(i, i)];
-  if (!live) return;
-  if (n_iters) n_iters[b] = iters;
-  if (ALL) {
-    int id[4];
-    small_sort_ids<4, T>(ev, SORT_DECREASING_EVALS, id);
+    for (int i = 0; i < 4; ++i) ev[i] = m[SmallShape<4>::tri(i, i)];
+    if (!live) return;
+    if (n_iters) n_iters[b] = iters;
+    if (ALL) {
+      int pos[4];
+      small_sort_positions<4, T>(ev, SORT_DECREASING_EVALS, pos);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      int pos = r;
+      for (int r = 0; r < 4; ++r) {
+        if (SOA) lambda[(long long)pos[r] * batch + b] = ev[r]; else lambda[b * 4 + pos[r]] = ev[r];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pos = (id[k] == r) ? k : pos;
-      if (SOA) lambda[(long long)pos * batch + b] = ev[r]; else lambda[b * 4 + pos] = ev[r];
+        for (int v = 0; v < 4; ++v) {
+          if (SOA) quat[((long long)pos[r] * 4 + v) * batch + b] = e[r * 4 + v];
+          else quat[b * 16 + pos[r] * 4 + v] = e[r * 4 + v];
+        }
+      }
+    } else {
+      // first maximum, as position 0 of the reference's decreasing selection sort (:483-487)
+      T best = ev[0];
+      int imax = 0;
+#pragma unroll
+      for (int i = 1; i < 4; ++i) { const bool gt = ev[i] > best; best = gt ? ev[i] : best; imax = gt ? i : imax; }
+      T q[4];
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        if (SOA) quat[((long long)pos * 4 + v) * batch + b] = e[r * 4 + v];
-        else quat[b * 16 + pos * 4 + v] = e[r * 4 + v];
+        q[v] = e[v];
+#pragma unroll
+        for (int r = 1; r < 4; ++r) q[v] = (imax == r) ? e[r * 4 + v] : q[v];
+      }
+      const bool flip = q[0] < T(0);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) q[v] = flip ? -q[v] : q[v];
+      lambda[b] = best;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        if (SOA) quat[(long long)v * batch + b] = q[v]; else quat[b * 4 + v] = q[v];
       }
     }
-  } else {
-    // first maximum, as position 0 of the reference's decreasing selection sort (:483-487)
-    T best = ev[0];
-    int imax = 0;
-#pragma unroll
-    for (int i = 1; i < 4; ++i) { const bool gt = ev[i] > best; best = gt ? ev[i] : best; imax = gt ? i : imax; }
-    T q[4];
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      q[v] = e[v];
-#pragma unroll
-      for (int r = 1; r < 4; ++r) q[v] = (imax == r) ? e[r * 4 + v] : q[v];
-    }
-    const bool flip = q[0] < T(0);
-#pragma unroll
-    for (int v = 0; v < 4; ++v) q[v] = flip ? -q[v] : q[v];
-    lambda[b] = best;
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      if (SOA) quat[(long long)v * batch + b] = q[v]; else quat[b * 4 + v] = q[v];
-    }
-  }
+  };
+  small_solve<4, T, true>(max_num_sweeps, load, emit);
 }
 
 // inertia6 = (Ixx, Iyy, Izz, Iyz, Ixz, Ixy); moments decreasing; axes[i*3 + k] = component i
@@ -99,54 +100,44 @@ jpd_inertia_kernel(const T* __restrict__ inertia6, T* __restrict__ moments, T* _
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = gid < batch;
   const long long b = live ? gid : batch - 1;
-  T I[6];
+  auto load = [&](T (&m)[6]) {
+    T I[6];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) I[k] = SOA ? __ldg(inertia6 + (long long)k * batch + b) : __ldg(inertia6 + b * 6 + k);
-  T m[6], e[9];
-  m[0] = I[0]; m[1] = I[5]; m[2] = I[4];   // (0,0) (0,1) (0,2)
-  m[3] = I[1]; m[4] = I[3];                // (1,1) (1,2)
-  m[5] = I[2];                             // (2,2)
-  const int iters = small_solve<3, T, true>(m, e, max_num_sweeps);
-  T ev[3];
+    for (int k = 0; k < 6; ++k) I[k] = SOA ? __ldg(inertia6 + (long long)k * batch + b) : __ldg(inertia6 + b * 6 + k);
+    m[0] = I[0]; m[1] = I[5]; m[2] = I[4];   // (0,0) (0,1) (0,2)
+    m[3] = I[1]; m[4] = I[3];                // (1,1) (1,2)
+    m[5] = I[2];                             // (2,2)
+  };
+  auto emit = [&](const T (&m)[6], const T (&e)[9], int iters) {
+    T ev[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) ev[i] = m[SmallShape<3>::tri(i, i)];
-  int id[3];
-  small_sort_ids<3, T>(ev, SORT_DECREASING_EVALS, id);
-  // gather the sorted rows through selects (registers cannot be indexed dynamically)
-  T w[3], ax[9];
+    for (int i = 0; i < 3; ++i) ev[i] = m[SmallShape<3>::tri(i, i)];
+    // Destinations are permuted, not data (no gather through selects or local memory):
+    // source row r is principal axis pos[r].  Right-handed frame: ez <- -ez if
+    // (ex x ey) . ez < 0, i.e. if det(sorted rows) = det(e) * sign(permutation) < 0.
+    int pos[3];
+    small_sort_positions<3, T>(ev, SORT_DECREASING_EVALS, pos);
+    const T cx = e[1] * e[5] - e[2] * e[4];
+    const T cy = e[2] * e[3] - e[0] * e[5];
+    const T cz = e[0] * e[4] - e[1] * e[3];
+    const bool det_neg = (cx * e[6] + cy * e[7] + cz * e[8]) < T(0);
+    const bool odd = ((pos[0] > pos[1]) != (pos[0] > pos[2])) != (pos[1] > pos[2]);
+    const bool flip = det_neg != odd;
+    if (!live) return;
+    if (n_iters) n_iters[b] = iters;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    w[k] = ev[0];
+    for (int r = 0; r < 3; ++r) {
+      if (SOA) moments[(long long)pos[r] * batch + b] = ev[r]; else moments[b * 3 + pos[r]] = ev[r];
+      const bool neg = flip && pos[r] == 2;
 #pragma unroll
-    for (int v = 0; v < 3; ++v) ax[k * 3 + v] = e[v];
-#pragma unroll
-    for (int r = 1; r < 3; ++r) {
-      const bool hit = id[k] == r;
-      w[k] = hit ? ev[r] : w[k];
-#pragma unroll
-      for (int v = 0; v < 3; ++v) ax[k * 3 + v] = hit ? e[r * 3 + v] : ax[k * 3 + v];
+      for (int i = 0; i < 3; ++i) {
+        const T val = neg ? -e[r * 3 + i] : e[r * 3 + i];
+        if (SOA) axes[((long long)(i * 3) + pos[r]) * batch + b] = val;
+        else axes[b * 9 + i * 3 + pos[r]] = val;
+      }
     }
-  }
-  // right-handed frame: ez <- -ez if (ex x ey) . ez < 0
-  const T cx = ax[1] * ax[5] - ax[2] * ax[4];
-  const T cy = ax[2] * ax[3] - ax[0] * ax[5];
-  const T cz = ax[0] * ax[4] - ax[1] * ax[3];
-  const bool flip = (cx * ax[6] + cy * ax[7] + cz * ax[8]) < T(0);
-#pragma unroll
-  for (int v = 0; v < 3; ++v) ax[6 + v] = flip ? -ax[6 + v] : ax[6 + v];
-  if (!live) return;
-  if (n_iters) n_iters[b] = iters;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    if (SOA) moments[(long long)k * batch + b] = w[k]; else moments[b * 3 + k] = w[k];
-  }
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      if (SOA) axes[(long long)(i * 3 + k) * batch + b] = ax[k * 3 + i];
-      else axes[b * 9 + i * 3 + k] = ax[k * 3 + i];
-    }
+  };
+  small_solve<3, T, true>(max_num_sweeps, load, emit);
 }
 
 #endif  // __CUDACC__

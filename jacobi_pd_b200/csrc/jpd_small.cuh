@@ -25,6 +25,13 @@
 //    pair whose x still underflowed.
 //  * Upper triangle only (as the reference reads only mat[i][j], j>=i, :167-171);
 //    eigenvectors are rows (:69).
+//  * Round 2 (instruction diet, DESIGN.md "tier 1"): the skip test of jacobi_pd.hpp:191 is
+//    evaluated ONCE per sweep (small_status), not again per pair: inside a sweep every pair
+//    whose off-diagonal entry is nonzero is rotated -- a pair the test would have skipped gets
+//    a rotation that is the identity to working precision, which is what the reference's
+//    `M[i][j] = 0` (:192) does to it as well.  The diagonal lives HALVED in registers
+//    (exact), which removes two FP64 instructions from every rotation (see
+//    small_rotate_pair).
 //  * Sort = the reference's selection sort replayed on (key,id) pairs with static
 //    indices, so ties resolve exactly as SortRows does.
 #pragma once
@@ -56,7 +63,28 @@ template <typename T> struct SmallRange {
   static constexpr int kHi = Fp<T>::kBias + Fp<T>::kSafe;             // entries <  2^481
   static constexpr int kXMin = Fp<T>::kBias - 2 * Fp<T>::kSafe + Fp<T>::kSafe / 8;  // x >= 2^-900
   static constexpr int kXMax = Fp<T>::kBias + 2 * Fp<T>::kSafe + Fp<T>::kSafe / 8;  // x <  2^1020
+  // added to every x (small_rotate_pair): 2^-1000 (fp64) / 2^-120 (fp32), a normal number that
+  // is below half an ulp of every x inside the window
+  JPD_HD static T tiny() { return pow2_from_field(sizeof(T) == 8 ? 23 : 7, T(0)); }
 };
+
+// the word that holds sign and exponent, as is (callers know x >= 0 or do not care)
+JPD_HD int high_word(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2hiint(x);
+#else
+  std::uint64_t u; std::memcpy(&u, &x, 8);
+  return (int)(u >> 32);
+#endif
+}
+JPD_HD int high_word(float x) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(x);
+#else
+  std::uint32_t u; std::memcpy(&u, &x, 4);
+  return (int)u;
+#endif
+}
 
 // |x| as an ordered integer: the high word of a double (the whole word of a float) with
 // the sign bit cleared grows monotonically with |x|, so magnitudes can be compared and
@@ -84,12 +112,40 @@ template <> struct KeyShift<float>  { static constexpr int value = 23; };
 // Skip test of the reference (jacobi_pd.hpp:191: a is below half an ulp of BOTH diagonal
 // entries) evaluated as  |a| * 2^(kMant+2) <= min(|mii|,|mjj|)  on abs_key()s.  The bound is
 // inside the reference's skip region, so a pair the reference would rotate is never skipped.
+// The diagonal is passed HALVED (h = m/2), hence kMant+1; the key is clamped at 0 so that an
+// exact zero off-diagonal (key 0) is never flagged, whatever the diagonal.  (Entries below
+// 2^-1042 in magnitude -- high word 0 -- count as zero here.)
 template <typename T>
-JPD_HD bool key_needs_rotation(int ka, bool a_is_zero, int kii, int kjj) {
-  const int kmin = kii < kjj ? kii : kjj;
-  // (kmin - shift rather than ka + shift: the latter overflows int for |a| > 2^970)
-  const int lowered = kmin - ((Fp<T>::kMantBits + 2) << KeyShift<T>::value);
-  return !a_is_zero & (ka > lowered);
+JPD_HD int diag_skip_key(T half_diag) {
+  const int lowered = abs_key(half_diag) - ((Fp<T>::kMantBits + 1) << KeyShift<T>::value);
+  return lowered > 0 ? lowered : 0;
+}
+
+// (2w)^-1/2 for w in [1, 2] WITHOUT forming 2w: the seed comes from the high word with the
+// exponent field bumped (one integer add), and the cubic correction of rsqrt_correct() is
+// rewritten in eh = e/2 = 1/2 - w z^2:  z (1 + e/2 + 3/8 e^2) = z + (1 + 3/2 eh) (eh z).
+JPD_HD double rsqrt_refined_of_double(double w) {
+#if defined(__CUDA_ARCH__)
+  double z;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(z) : "d"(__hiloint2double(__double2hiint(w) + 0x00100000, 0)));
+  const double wz = w * z;
+  const double eh = __fma_rn(-wz, z, 0.5);
+  const double r2 = __fma_rn(1.5, eh, 1.0);
+  const double ehz = eh * z;
+  return __fma_rn(r2, ehz, z);
+#else
+  return 1.0 / std::sqrt(2.0 * w);
+#endif
+}
+JPD_HD float rsqrt_refined_of_double(float w) {
+#if defined(__CUDA_ARCH__)
+  float z;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(z) : "f"(__int_as_float(__float_as_int(w) + 0x00800000)));
+  const float eh = __fmaf_rn(-(w * z), z, 0.5f);
+  return __fmaf_rn(z, eh, z);              // one Newton step: z (1 + e/2)
+#else
+  return (float)(1.0 / std::sqrt(2.0 * (double)w));
+#endif
 }
 
 // Rows I and J of E, column W onwards, using what is known about the entries at compile time.
@@ -113,9 +169,16 @@ JPD_HD void small_rotate_rows(T (&e)[N * N], T c, T s) {
   }
 }
 
-// One Jacobi rotation of the static pair (I,J), I<J, branch-free.  The skip test is taken
-// on the CURRENT entries (re-using the sweep-start flags instead was measured: stale flags
-// cost ~4% more rotations and a longer warp-max sweep count).
+// One Jacobi rotation of the static pair (I,J), I<J, branch-free.
+//
+// m holds the diagonal HALVED: hI = mII/2, hJ = mJJ/2.  With D = hJ - hI = d/2:
+//     x = a^2 + D^2 = (d^2 + 4a^2)/4,   P = x^-1/2 = 2/sqrt(d^2+4a^2)
+//     w = 1 + |D| P = 1 + cos 2θ = 2 cos^2 θ   (one FMA; in [1,2])
+//     U = (2w)^-1/2 = 1/(2 cos θ)              (2w: integer add on the exponent)
+//     c = w U,   s = (a P) U sgn(d),   g = s U = tan θ / 2
+//     hI' = hI - g a,  hJ' = hJ + g a          (jacobi_pd.hpp:337-338, halved)
+// Same angle as CalcRot (jacobi_pd.hpp:233-256: |t| <= 1).  18 FP64-pipe instructions
+// (2 refined rsqrt = 10, plus 8) + 2 for the diagonal; no division.
 //
 // NZ / ONE: compile-time knowledge about E during the FIRST sweep, which starts from the
 // identity (bit i*N+w set = entry (i,w) may be nonzero / is exactly 1).  Rows that are still
@@ -142,62 +205,45 @@ template <int N> JPD_CX constexpr unsigned long long mask_after_one(unsigned lon
 }
 
 template <int N, typename T, bool EVECS, bool SCALED, int I, int J, unsigned long long NZ, unsigned long long ONE>
-JPD_HD void small_rotate_pair(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N : 1],
-                              int& n_rot, bool& guard_hit) {
+JPD_HD void small_rotate_pair(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N : 1], bool& out_of_range) {
   using Sh = SmallShape<N>;
   const T a = m[Sh::tri(I, J)];
-  const T mii = m[Sh::tri(I, I)];
-  const T mjj = m[Sh::tri(J, J)];
-  const bool flagged = key_needs_rotation<T>(abs_key(a), is_zero(a), abs_key(mii), abs_key(mjj));
-  T d = mjj - mii;
+  const T hi = m[Sh::tri(I, I)];
+  const T hj = m[Sh::tri(J, J)];
+  const bool a_nz = !is_zero(a);
+  T dl = hj - hi;
   T as = a;
-  // sign(t) = sign(a) sign(d); the reference takes t = +1 when d == 0 whatever the sign of
-  // a (jacobi_pd.hpp:237-239) -- kept, so that n == 2 agrees with it even unsorted.
-  const T sign_src = is_zero(d) ? a : d;
-  if (SCALED) rescale_for_rotation(d, as);
-  // ---- rotation_from_scaled() of jpd_common.cuh, inlined so the guard can look at x
-  const T a2 = as + as;
-  const T x = jfma(a2, a2, d * d);
-  // x == 0 (pair already exactly diagonal), or x under/overflowed in the un-rescaled
-  // variant: leave the pair alone in this sweep; small_solve() then switches the warp to
-  // the rescaling variant, which has no such limit.
-  const int kx = abs_key(x);
-  const bool x_ok = SCALED ? (kx != 0)
-                           : ((unsigned)(kx - (SmallRange<T>::kXMin << KeyShift<T>::value)) <
-                              (unsigned)((SmallRange<T>::kXMax - SmallRange<T>::kXMin) << KeyShift<T>::value));
-  const bool need = flagged & x_ok;
-  guard_hit = guard_hit | (flagged & !x_ok);
-#if defined(JPD_SELECT_CST)
+  // sign(t) = sign(a) sign(d).  For d == 0 the reference takes t = +1 whatever the sign of a
+  // (jacobi_pd.hpp:237-239): kept for N == 2, where the rotation order IS the reference's, so
+  // that even the unsorted output agrees; for N > 2 (d == +0) t = sign(a) -- either choice
+  // zeroes the pivot, and the unsorted order is implementation defined there anyway.
+  T sign_src = dl;
+  if constexpr (N == 2) sign_src = is_zero(dl) ? a : dl;
+  if (SCALED) rescale_for_rotation(dl, as);
+  // + tiny: x > 0 even for a pair that is exactly diagonal already (a = D = 0), so that P
+  // stays finite and s = g = 0 * P * U = 0 without a select.  tiny is far below the window
+  // in which the un-rescaled variant accepts x, and below 2^-900 of the rescaled x in [1,8).
+  const T x = jfma(as, as, jfma(dl, dl, SmallRange<T>::tiny()));
+  // Un-rescaled variant: a nonzero pivot whose x left the window in which squares neither
+  // overflow nor lose bits to underflow cannot be rotated here; small_solve() then discards
+  // this pass for the whole warp and repeats it with the rescaling variant.
+  if (!SCALED) {
+    const bool in_window = (unsigned)(high_word(x) - (SmallRange<T>::kXMin << KeyShift<T>::value)) <
+                           (unsigned)((SmallRange<T>::kXMax - SmallRange<T>::kXMin) << KeyShift<T>::value);
+    out_of_range = out_of_range | (a_nz & !in_window);
+  }
   const T p = rsqrt_refined(x);
-  const T rho = jabs(d) * p;
-  const T ap = xor_sign(as * p, sign_src);         // sin(2 theta) / 2 with the sign of t
-  const T v = jfma(half_const(T(0)), rho, T(0.5));  // cos^2(theta)
-  const T u = rsqrt_refined(v);
-  T c = v * u;
-  T s = ap * u;
-  T t = s * u;
-  c = need ? c : T(1);
-  s = need ? s : T(0);
-  t = need ? t : T(0);
-#else
-  // A pair that is left alone gets the exact identity through TWO selects: p = 0 makes
-  // rho = 0, v = 1/2 (finite whatever x was), s = t = (a * 0) * u = 0, and c is replaced by 1.
-  T p = rsqrt_refined(x);
-  p = need ? p : T(0);
-  const T rho = jabs(d) * p;
-  const T ap = xor_sign(as * p, sign_src);         // sin(2 theta) / 2 with the sign of t
-  const T v = jfma(half_const(T(0)), rho, T(0.5));  // cos^2(theta)
-  const T u = rsqrt_refined(v);
-  T c = v * u;
-  const T s = ap * u;
-  const T t = s * u;
-  c = need ? c : T(1);
-#endif
-  n_rot += need ? 1 : 0;
+  const T w = jfma(jabs(dl), p, T(1));
+  const T u = rsqrt_refined_of_double(w);
+  T c = w * u;
+  const T s = xor_sign(as * p, sign_src) * u;
+  const T g = s * u;
+  // a == 0: the exact identity (s = g = 0 already; c would only be 1 to an ulp)
+  c = a_nz ? c : T(1);
   // diagonal through t, pivot zeroed: jacobi_pd.hpp:337-338,347
-  m[Sh::tri(I, I)] = jfma(-t, a, mii);
-  m[Sh::tri(J, J)] = jfma(t, a, mjj);
-  m[Sh::tri(I, J)] = need ? T(0) : a;
+  m[Sh::tri(I, I)] = jfma(-g, a, hi);
+  m[Sh::tri(J, J)] = jfma(g, a, hj);
+  m[Sh::tri(I, J)] = T(0);
   // the two changed rows/columns, upper-triangle names: jacobi_pd.hpp:350-390
 #pragma unroll
   for (int k = 0; k < N; ++k) {
@@ -215,74 +261,103 @@ JPD_HD void small_rotate_pair(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N 
 // One full round-robin sweep, unrolled at compile time: pair P of kSteps*kHalf.
 template <int N, typename T, bool EVECS, bool SCALED, int P, unsigned long long NZ = kDenseMask,
           unsigned long long ONE = 0ull>
-JPD_HD void small_sweep_from(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N : 1],
-                             int& n_rot, bool& guard_hit) {
+JPD_HD void small_sweep_from(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N : 1], bool& out_of_range) {
   using Sh = SmallShape<N>;
   if constexpr (P < Sh::kSteps * Sh::kHalf) {
     constexpr int S = P / Sh::kHalf, K = P % Sh::kHalf;
     constexpr int A = Sh::player_a(S, K), B = Sh::player_b(S, K);
     if constexpr (A < N && B < N) {  // a pair with the dummy player (odd N) sits out
       constexpr int I = A < B ? A : B, J = A < B ? B : A;
-      small_rotate_pair<N, T, EVECS, SCALED, I, J, NZ, ONE>(m, e, n_rot, guard_hit);
+      small_rotate_pair<N, T, EVECS, SCALED, I, J, NZ, ONE>(m, e, out_of_range);
       small_sweep_from<N, T, EVECS, SCALED, P + 1, mask_after_nz<N>(NZ, I, J), mask_after_one<N>(ONE, I, J)>(
-          m, e, n_rot, guard_hit);
+          m, e, out_of_range);
     } else {
-      small_sweep_from<N, T, EVECS, SCALED, P + 1, NZ, ONE>(m, e, n_rot, guard_hit);
+      small_sweep_from<N, T, EVECS, SCALED, P + 1, NZ, ONE>(m, e, out_of_range);
     }
   }
 }
 
-// Sweep-start status of one lane: the skip test of every pair (in schedule order).
+// Sweep-start status of one lane: the skip test of every pair (m holds the halved diagonal).
 template <int N, typename T>
 JPD_HD bool small_status(const T (&m)[SmallShape<N>::kTri]) {
   using Sh = SmallShape<N>;
-  int key[Sh::kTri];
+  int kd[N];
 #pragma unroll
-  for (int k = 0; k < Sh::kTri; ++k) key[k] = abs_key(m[k]);
+  for (int i = 0; i < N; ++i) kd[i] = diag_skip_key<T>(m[Sh::tri(i, i)]);
   bool any_need = false;
 #pragma unroll
-  for (int P = 0; P < Sh::kSteps * Sh::kHalf; ++P) {
-    const int A = Sh::player_a(P / Sh::kHalf, P % Sh::kHalf), B = Sh::player_b(P / Sh::kHalf, P % Sh::kHalf);
-    if (A < N && B < N) {
-      const int i = A < B ? A : B, j = A < B ? B : A;
-      any_need = any_need | key_needs_rotation<T>(key[Sh::tri(i, j)], is_zero(m[Sh::tri(i, j)]),
-                                                  key[Sh::tri(i, i)], key[Sh::tri(j, j)]);
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = i + 1; j < N; ++j) {
+      const int ka = abs_key(m[Sh::tri(i, j)]);
+      any_need = any_need | (ka > kd[i]) | (ka > kd[j]);   // ka > min(kd[i], kd[j])
     }
-  }
   return any_need;
 }
 
-// Diagonalise the register-resident matrix. Returns the reference's return value:
+// One pass over the register-resident matrix.  Returns the reference's return value:
 // rotations + 1 (> 0) once a sweep starts with nothing left to rotate, 0 if that was not
 // observed within max_num_sweeps sweeps and n > 1 (jacobi_pd.hpp:214-219).
-template <int N, typename T, bool EVECS>
-JPD_HD int small_solve(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N : 1], int max_num_sweeps) {
+// SCALED = false is the common pass; a lane that meets a pivot it cannot rotate without
+// rescaling sets out_of_range (its own result is then garbage) and no longer counts in the
+// warp's vote to go on sweeping.
+template <int N, typename T, bool EVECS, bool SCALED>
+JPD_HD int small_solve_pass(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N : 1], int max_num_sweeps,
+                            bool& out_of_range) {
   if (EVECS) {
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
       for (int j = 0; j < N; ++j) e[i * N + j] = (i == j) ? T(1) : T(0);  // :172-178
   }
+  out_of_range = false;
   if (N == 1) return 1;
+#pragma unroll
+  for (int i = 0; i < N; ++i) m[SmallShape<N>::tri(i, i)] *= T(0.5);  // exact (see small_rotate_pair)
+  constexpr int kPairs = N * (N - 1) / 2;
   int n_rot = 0;
   bool converged = false;
-  bool rescale = false;  // warp-uniform: a lane met an x outside the safe window
   for (int sweep = 0; sweep < max_num_sweeps; ++sweep) {
     const bool any_need = small_status<N, T>(m);
     converged = converged || !any_need;
-    if (!JPD_WARP_ANY(any_need)) break;
-    bool guard_hit = false;
-#if defined(JPD_NO_FIRST_SWEEP_SPARSITY)
-    if (rescale) small_sweep_from<N, T, EVECS, true, 0>(m, e, n_rot, guard_hit);
-#else
-    // sweep 0 starts from E = I (and `rescale` is still false): sparse eigenvector update
-    if (sweep == 0) small_sweep_from<N, T, EVECS, false, 0, identity_mask<N>(), identity_mask<N>()>(m, e, n_rot, guard_hit);
-    else if (rescale) small_sweep_from<N, T, EVECS, true, 0>(m, e, n_rot, guard_hit);
-#endif
-    else         small_sweep_from<N, T, EVECS, false, 0>(m, e, n_rot, guard_hit);
-    rescale = rescale || JPD_WARP_ANY(guard_hit);
+    // a lane that already gave up (out_of_range) does not keep its warp sweeping
+    if (!JPD_WARP_ANY(any_need && !out_of_range)) break;
+    // rotations attempted: every pair of a sweep this lane still needed (for n = 2 exactly the
+    // reference's count; the n_iters contract is "> 0 iff converged", jacobi_pd.hpp:73-74)
+    n_rot += converged ? 0 : kPairs;
+    if (SCALED) {
+      small_sweep_from<N, T, EVECS, true, 0>(m, e, out_of_range);
+    } else {
+      // sweep 0 starts from E = I: sparse eigenvector update
+      if (sweep == 0) small_sweep_from<N, T, EVECS, false, 0, identity_mask<N>(), identity_mask<N>()>(m, e, out_of_range);
+      else            small_sweep_from<N, T, EVECS, false, 0>(m, e, out_of_range);
+    }
   }
+#pragma unroll
+  for (int i = 0; i < N; ++i) m[SmallShape<N>::tri(i, i)] *= T(2);
   return converged ? n_rot + 1 : 0;
+}
+
+// Diagonalise one register-resident matrix per lane: `load(m)` fills the upper triangle,
+// `emit(m, e, n_iters)` consumes the result (m: eigenvalues on the diagonal, e: eigenvector
+// rows).  If a lane of the warp met a pivot that needs rescaling (huge, tiny or denormal
+// entries -- rare), the lanes that did NOT emit their finished result at once and only the
+// others reload and repeat with the rescaling variant: a matrix never changes the bits of its
+// neighbours' results, and no state has to be kept in registers for the rare case.
+template <int N, typename T, bool EVECS, typename Load, typename Emit>
+JPD_HD void small_solve(int max_num_sweeps, Load load, Emit emit) {
+  T m[SmallShape<N>::kTri];
+  T e[EVECS ? N * N : 1];
+  load(m);
+  bool out_of_range;
+  int iters = small_solve_pass<N, T, EVECS, false>(m, e, max_num_sweeps, out_of_range);
+  if (JPD_WARP_ANY(out_of_range)) {
+    if (!out_of_range) { emit(m, e, iters); return; }
+    bool unused;
+    load(m);
+    iters = small_solve_pass<N, T, EVECS, true>(m, e, max_num_sweeps, unused);
+  }
+  emit(m, e, iters);
 }
 
 // Replay of SortRows (jacobi_pd.hpp:477-508) on keys with static indices; id[k] ends up
@@ -324,6 +399,65 @@ JPD_HD void small_sort_ids(const T (&ev)[N], int sort_criteria, int (&id)[N]) {
   }
 }
 
+// Sort key: the reference's four orderings (jacobi_pd.hpp:483-499) all become "larger key
+// first" after clearing and/or flipping the sign bit -- integer pipe, one LOP3 per key.
+JPD_HD double sort_key(double v, int clear_mask, int flip_mask) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double((__double2hiint(v) & clear_mask) ^ flip_mask, __double2loint(v));
+#else
+  std::uint64_t u; std::memcpy(&u, &v, 8);
+  u = (u & (((std::uint64_t)(std::uint32_t)clear_mask << 32) | 0xffffffffull)) ^ ((std::uint64_t)(std::uint32_t)flip_mask << 32);
+  double r; std::memcpy(&r, &u, 8); return r;
+#endif
+}
+JPD_HD float sort_key(float v, int clear_mask, int flip_mask) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float((__float_as_int(v) & clear_mask) ^ flip_mask);
+#else
+  std::uint32_t u; std::memcpy(&u, &v, 4);
+  u = (u & (std::uint32_t)clear_mask) ^ (std::uint32_t)flip_mask;
+  float r; std::memcpy(&r, &u, 4); return r;
+#endif
+}
+
+// pos[r] = output position of source slot r under SortRows (jacobi_pd.hpp:477-508).
+// Without ties among the keys the selection sort's result is simply the ranking, which costs
+// two instructions per pair; a lane that does hold equal keys (exactly repeated eigenvalues,
+// +-lambda under the ABS criteria) replays the reference's selection sort, whose tie order is
+// not the stable one.  Returns false (pos = identity) for DO_NOT_SORT / unknown criteria.
+template <int N, typename T>
+JPD_HD bool small_sort_positions(const T (&ev)[N], int sort_criteria, int (&pos)[N]) {
+#pragma unroll
+  for (int r = 0; r < N; ++r) pos[r] = r;
+  if (sort_criteria < SORT_DECREASING_EVALS || sort_criteria > SORT_INCREASING_ABS_EVALS)
+    return false;  // no-op (jacobi_pd.hpp:500-501)
+  const int clear_mask = sort_criteria >= SORT_DECREASING_ABS_EVALS ? 0x7fffffff : -1;
+  const int flip_mask = (sort_criteria == SORT_INCREASING_EVALS || sort_criteria == SORT_INCREASING_ABS_EVALS)
+                            ? (int)0x80000000 : 0;
+  T key[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) { key[k] = sort_key(ev[k], clear_mask, flip_mask); pos[k] = 0; }
+  bool tie = false;
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+#pragma unroll
+    for (int r = k + 1; r < N; ++r) {
+      const bool first = key[k] >= key[r];
+      tie = tie | (key[k] == key[r]);
+      pos[r] += first ? 1 : 0;
+      pos[k] += first ? 0 : 1;
+    }
+  if (tie) {
+    int id[N];
+    small_sort_ids<N, T>(ev, sort_criteria, id);
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+      for (int k = 0; k < N; ++k) pos[r] = (id[k] == r) ? k : pos[r];
+  }
+  return true;
+}
+
 #if defined(__CUDACC__)
 
 #ifndef JPD_SMALL_THREADS
@@ -352,55 +486,44 @@ jpd_small_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict
   const bool live = gid < batch;
   const long long b = live ? gid : batch - 1;  // tail lanes shadow the last matrix (no stores)
 
-  T m[Sh::kTri];
-  T e[EVECS ? N * N : 1];
+  auto load = [&](T (&m)[Sh::kTri]) {
 #pragma unroll
-  for (int i = 0; i < N; ++i)
+    for (int i = 0; i < N; ++i)
 #pragma unroll
-    for (int j = i; j < N; ++j)
-      m[Sh::tri(i, j)] = SOA ? __ldg(mat + (long long)(i * N + j) * batch + b)
-                             : __ldg(mat + b * (N * N) + (i * N + j));
-
-  const int iters = small_solve<N, T, EVECS>(m, e, max_num_sweeps);
-
-  T ev[N];
+      for (int j = i; j < N; ++j)
+        m[Sh::tri(i, j)] = SOA ? __ldg(mat + (long long)(i * N + j) * batch + b)
+                               : __ldg(mat + b * (N * N) + (i * N + j));
+  };
+  auto emit = [&](const T (&m)[Sh::kTri], const T (&e)[EVECS ? N * N : 1], int iters) {
+    T ev[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) ev[i] = m[Sh::tri(i, i)];  // :207-209
-  int id[N];
-  small_sort_ids<N, T>(ev, sort_criteria, id);
-  const bool sorted = sort_criteria >= SORT_DECREASING_EVALS && sort_criteria <= SORT_INCREASING_ABS_EVALS;
-
-  if (!live) return;
-  if (n_iters) n_iters[b] = iters;
-  // The sort permutes DESTINATIONS, not data: source row r goes to output row pos[r].  (Moving
-  // the rows through selects or a local-memory table costs ~200 more instructions per matrix;
-  // the scattered 8-byte stores of one warp still fill whole sectors over the N rows and are
-  // merged in L2 -- DRAM traffic stays at the algorithmic 8(N+N^2)+4 bytes, see profiles/.)
-  int pos[N];
-#pragma unroll
-  for (int r = 0; r < N; ++r) {
-    pos[r] = r;
-    if (sorted) {
-#pragma unroll
-      for (int k = 0; k < N; ++k) pos[r] = (id[k] == r) ? k : pos[r];
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < N; ++r) {
-    if (SOA) evals[(long long)pos[r] * batch + b] = ev[r];
-    else evals[b * N + pos[r]] = ev[r];
-  }
-  if (EVECS) {
+    for (int i = 0; i < N; ++i) ev[i] = m[Sh::tri(i, i)];  // :207-209
+    // The sort permutes DESTINATIONS, not data: source row r goes to output row pos[r].  (Moving
+    // the rows through selects or a local-memory table costs ~200 more instructions per matrix;
+    // the scattered 8-byte stores of one warp still fill whole sectors over the N rows and are
+    // merged in L2 -- DRAM traffic stays at the algorithmic 8(N+N^2)+4 bytes, see profiles/.)
+    int pos[N];
+    small_sort_positions<N, T>(ev, sort_criteria, pos);
+    if (!live) return;
+    if (n_iters) n_iters[b] = iters;
 #pragma unroll
     for (int r = 0; r < N; ++r) {
-      T* row = SOA ? evecs + (long long)pos[r] * N * batch + b : evecs + b * (N * N) + pos[r] * N;
+      if (SOA) evals[(long long)pos[r] * batch + b] = ev[r];
+      else evals[b * N + pos[r]] = ev[r];
+    }
+    if (EVECS) {
 #pragma unroll
-      for (int v = 0; v < N; ++v) {
-        if (SOA) row[(long long)v * batch] = e[r * N + v];
-        else row[v] = e[r * N + v];
+      for (int r = 0; r < N; ++r) {
+        T* row = SOA ? evecs + (long long)pos[r] * N * batch + b : evecs + b * (N * N) + pos[r] * N;
+#pragma unroll
+        for (int v = 0; v < N; ++v) {
+          if (SOA) row[(long long)v * batch] = e[r * N + v];
+          else row[v] = e[r * N + v];
+        }
       }
     }
-  }
+  };
+  small_solve<N, T, EVECS>(max_num_sweeps, load, emit);
 }
 
 #endif  // __CUDACC__

@@ -10,25 +10,30 @@ template <int N, typename T>
 void run(const T* mat, T* evals, T* evecs, int* iters, long long batch, int sort, int calc, int sweeps) {
   using Sh = jpd::SmallShape<N>;
   for (long long b = 0; b < batch; ++b) {
-    T m[Sh::kTri];
-    for (int i = 0; i < N; ++i)
-      for (int j = i; j < N; ++j) m[Sh::tri(i, j)] = mat[b * N * N + i * N + j];
-    T ev[N]; int id[N]; int it;
+    auto load = [&](T (&mm)[Sh::kTri]) {
+      for (int i = 0; i < N; ++i)
+        for (int j = i; j < N; ++j) mm[Sh::tri(i, j)] = mat[b * N * N + i * N + j];
+    };
     if (calc) {
-      T e[N * N];
-      it = jpd::small_solve<N, T, true>(m, e, sweeps);
-      for (int i = 0; i < N; ++i) ev[i] = m[Sh::tri(i, i)];
-      jpd::small_sort_ids<N, T>(ev, sort, id);
-      for (int k = 0; k < N; ++k)
-        for (int v = 0; v < N; ++v) evecs[b * N * N + k * N + v] = e[id[k] * N + v];
+      jpd::small_solve<N, T, true>(sweeps, load, [&](const T (&m)[Sh::kTri], const T (&e)[N * N], int it) {
+        T ev[N]; int id[N];
+        for (int i = 0; i < N; ++i) ev[i] = m[Sh::tri(i, i)];
+        jpd::small_sort_ids<N, T>(ev, sort, id);
+        for (int k = 0; k < N; ++k) {
+          evals[b * N + k] = ev[id[k]];
+          for (int v = 0; v < N; ++v) evecs[b * N * N + k * N + v] = e[id[k] * N + v];
+        }
+        if (iters) iters[b] = it;
+      });
     } else {
-      T e[1];
-      it = jpd::small_solve<N, T, false>(m, e, sweeps);
-      for (int i = 0; i < N; ++i) ev[i] = m[Sh::tri(i, i)];
-      jpd::small_sort_ids<N, T>(ev, sort, id);
+      jpd::small_solve<N, T, false>(sweeps, load, [&](const T (&m)[Sh::kTri], const T (&)[1], int it) {
+        T ev[N]; int id[N];
+        for (int i = 0; i < N; ++i) ev[i] = m[Sh::tri(i, i)];
+        jpd::small_sort_ids<N, T>(ev, sort, id);
+        for (int k = 0; k < N; ++k) evals[b * N + k] = ev[id[k]];
+        if (iters) iters[b] = it;
+      });
     }
-    for (int k = 0; k < N; ++k) evals[b * N + k] = ev[id[k]];
-    if (iters) iters[b] = it;
   }
 }
 template <typename T>
