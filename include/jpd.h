@@ -123,7 +123,7 @@ JPD_API int jpd_diagonalize_batched_host_multi_f32(const float* h_mat, float* h_
  *
  * colvars optimal rotation: d_corr holds 3x3 correlation matrices C = sum_k x_k y_k^T,
  * row-major (xx xy xz yx yy yz zx zy zz): AoS corr[b*9 + e] or SoA corr[e*batch + b].  The
- * 4x4 overlap matrix S (Horn 1987; the formula of jpd_fill_synthetic kind 1) is
+ * 4x4 overlap matrix S (Horn 1987; the formula of jpd_fill_synthetic kind 1, include/jpd_bench.h) is
  * diagonalised as Diagonalize(S, ..., SORT_DECREASING_EVALS) would (jacobi_pd.hpp:159-220).
  *   all_eigenpairs == 0: d_lambda[b] = largest eigenvalue, d_quat = its eigenvector with
  *                        q0 >= 0 (AoS quat[b*4 + v], SoA quat[v*batch + b])
@@ -162,23 +162,6 @@ JPD_API int jpd_convert_layout_f32(const void* d_src, int src_layout, float* d_d
 
 /* slice g of G of a batch: first index and length (the partition used above) */
 JPD_API void jpd_slice(long long batch, int n_parts, int part, long long* first, long long* count);
-
-/* ---- synthetic inputs (bench / tests; host twin: oracle/jpd_oracle.c) ---------------
- * Counter-based generator, identical bits on host and device:
- *   kind 0: upper-triangle entries iid U(-1,1), mirrored
- *   kind 1: n == 4, quaternion-superposition overlap matrix of a 3x3 U(-1,1) correlation
- * Writes matrices b0 .. b0+batch-1 of the stream at local indices 0..batch-1 (device ptr). */
-JPD_API int jpd_fill_synthetic_f64(double* d_mat, int n, long long batch, int layout, int kind,
-                           unsigned long long seed, long long b0, void* cuda_stream);
-JPD_API int jpd_fill_synthetic_f32(float* d_mat, int n, long long batch, int layout, int kind,
-                           unsigned long long seed, long long b0, void* cuda_stream);
-
-/* ---- FMA-pipe probe (bench only) -------------------------------------------------------
- * Launches a register-only stream of independent FMAs (elem_size 8 = DFMA, 4 = FFMA) and
- * returns how many FMAs it issues (negative on error); bench.py times it with CUDA events
- * to obtain the measured FP64/FP32 peak used as the FP-bound roofline denominator. */
-JPD_API long long jpd_fma_probe(int elem_size, int blocks, int threads, int iters, void* d_scratch,
-                                void* cuda_stream);
 
 /* ---- bookkeeping -------------------------------------------------------------------- */
 /* algorithmic bytes per matrix: elem*(n(n+1)/2 + n + (calc_evecs? n*n : 0)) + 4   */

@@ -17,43 +17,21 @@
 #include <thread>
 #include <vector>
 
-#include "jpd.h"
-#include "jpd_block.cuh"
-#include "jpd_small.cuh"
-#include "jpd_warp.cuh"
-#include "jpd_cta.cuh"
-#include "jpd_cluster.cuh"
-#include "jpd_fused.cuh"
-#include "jpd_layout.cuh"
+#include "jpd_internal.h"
+
+namespace jpd_host {
 
 namespace {
-
-using namespace jpd;
-
-constexpr int kSmallMaxN = 6;      // tier 1 upper bound (registers only)
-constexpr int kSmallThreads = JPD_SMALL_THREADS;
-constexpr int kMaxDevices = 64;
-
 thread_local std::string g_last_cuda_error;
-std::atomic<long long> g_launches{0};
-
-#define JPD_CK(expr)                                                                   \
-  do {                                                                                 \
-    cudaError_t _e = (expr);                                                           \
-    if (_e != cudaSuccess) {                                                           \
-      g_last_cuda_error = std::string(#expr) + ": " + cudaGetErrorString(_e);          \
-      return JPD_ERR_CUDA;                                                             \
-    }                                                                                  \
-  } while (0)
-
-struct DeviceInfo {
-  bool ready = false;
-  int sm_count = 148;
-  int smem_optin = 232448;
-  bool pool_tuned = false;
-};
 DeviceInfo g_dev[kMaxDevices];
 std::mutex g_dev_mutex;
+}  // namespace
+
+std::atomic<long long> g_launches{0};
+
+void set_last_cuda_error(const char* expr, cudaError_t e) {
+  g_last_cuda_error = std::string(expr) + ": " + cudaGetErrorString(e);
+}
 
 int device_info(int dev, DeviceInfo* out) {
   if (dev < 0 || dev >= kMaxDevices) return JPD_ERR_INVALID_ARG;
@@ -68,171 +46,25 @@ int device_info(int dev, DeviceInfo* out) {
   return JPD_OK;
 }
 
-// ------------------------------------------------------------------ tier 1 launch
-template <int N, typename T>
-int launch_small(const T* mat, T* evals, T* evecs, int* iters, long long batch, int layout,
-                 int sort, int calc, int sweeps, cudaStream_t st) {
-  const long long blocks = (batch + kSmallThreads - 1) / kSmallThreads;
-  if (blocks > 0x7fffffffLL) return JPD_ERR_UNSUPPORTED;
-  const dim3 grid((unsigned)blocks), block(kSmallThreads);
-  if (layout == JPD_LAYOUT_SOA) {
-    if (calc) jpd_small_kernel<N, T, true, true><<<grid, block, 0, st>>>(mat, evals, evecs, iters, batch, sort, sweeps);
-    else      jpd_small_kernel<N, T, true, false><<<grid, block, 0, st>>>(mat, evals, evecs, iters, batch, sort, sweeps);
-  } else {
-    if (calc) jpd_small_kernel<N, T, false, true><<<grid, block, 0, st>>>(mat, evals, evecs, iters, batch, sort, sweeps);
-    else      jpd_small_kernel<N, T, false, false><<<grid, block, 0, st>>>(mat, evals, evecs, iters, batch, sort, sweeps);
+void keep_freed_workspace_cached(int dev) {
+  if (dev < 0 || dev >= kMaxDevices) return;
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  if (g_dev[dev].pool_tuned) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  JPD_CK(cudaGetLastError());
-  return JPD_OK;
+  g_dev[dev].pool_tuned = true;
 }
 
-// ------------------------------------------------------------------ tier 2 launch (warp per matrix)
-constexpr int kWarpMaxN = 32;
-constexpr int kWarpThreads = JPD_WARP_THREADS;
+const char* last_cuda_error_cstr() { return g_last_cuda_error.c_str(); }
 
-template <typename T, int NP>
-int launch_warp(const T* mat, T* evals, T* evecs, int* iters, int n, long long batch, int layout,
-                int sort, int calc, int sweeps, cudaStream_t st) {
-  using Sh = WarpShape<NP>;
-  constexpr int warps = kWarpThreads / 32;
-  const long long per_block = (long long)warps * Sh::kGroups;
-  const long long blocks = (batch + per_block - 1) / per_block;
-  if (blocks > 0x7fffffffLL) return JPD_ERR_UNSUPPORTED;
-  const size_t smem = Sh::block_bytes(sizeof(T), warps);
-  const bool full = (n == NP);
-  auto kernel = calc ? (full ? jpd_warp_kernel<T, NP, true, true> : jpd_warp_kernel<T, NP, true, false>)
-                     : (full ? jpd_warp_kernel<T, NP, false, true> : jpd_warp_kernel<T, NP, false, false>);
-  if (smem > 48 * 1024)
-    JPD_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kernel<<<dim3((unsigned)blocks), dim3(kWarpThreads), smem, st>>>(
-      mat, evals, evecs, iters, n, batch, layout == JPD_LAYOUT_SOA ? 1 : 0, sort, sweeps);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  JPD_CK(cudaGetLastError());
-  return JPD_OK;
-}
+}  // namespace jpd_host
 
-// ------------------------------------------------------------------ tier 3 launch (CTA per matrix, E in registers)
-constexpr int kCtaMaxN = 128;
+namespace {
 
-template <typename T, int NPB>
-int launch_cta(const T* mat, T* evals, T* evecs, int* iters, int n, long long batch, int layout,
-               int sort, int calc, int sweeps, cudaStream_t st) {
-  using Sh = CtaShape<NPB>;
-  int dev = 0;
-  JPD_CK(cudaGetDevice(&dev));
-  DeviceInfo info;
-  int rc = device_info(dev, &info);
-  if (rc != JPD_OK) return rc;
-  const size_t smem = Sh::block_bytes(sizeof(T));
-  auto kernel = calc ? jpd_cta_kernel<T, NPB, true> : jpd_cta_kernel<T, NPB, false>;
-  if (smem > 48 * 1024)
-    JPD_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 1;
-  JPD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, Sh::kThreads, smem));
-  if (per_sm < 1) return JPD_ERR_UNSUPPORTED;
-  const long long grid = std::min<long long>(batch, (long long)per_sm * info.sm_count);
-  kernel<<<dim3((unsigned)grid), dim3(Sh::kThreads), smem, st>>>(
-      mat, evals, evecs, iters, n, batch, layout == JPD_LAYOUT_SOA ? 1 : 0, sort, sweeps);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  JPD_CK(cudaGetLastError());
-  return JPD_OK;
-}
-
-// ------------------------------------------------------------------ tier 4 launch (4-CTA cluster per matrix)
-constexpr int kClusterMaxN = ClusterShape::kN;
-
-template <typename T>
-int launch_cluster(const T* mat, T* evals, T* evecs, int* iters, int n, long long batch, int layout,
-                   int sort, int calc, int sweeps, cudaStream_t st) {
-  using Sh = ClusterShape;
-  const size_t smem = Sh::block_bytes(sizeof(T));
-  auto kernel = calc ? jpd_cluster_kernel<T, true> : jpd_cluster_kernel<T, false>;
-  JPD_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int max_clusters = 0;
-  {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(Sh::kCtas * 64);
-    cfg.blockDim = dim3(Sh::kThreads);
-    cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = Sh::kCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess || max_clusters < 1) {
-      (void)cudaGetLastError();
-      max_clusters = 32;
-    }
-  }
-  const long long clusters = std::min<long long>(batch, max_clusters);
-  kernel<<<dim3((unsigned)(clusters * Sh::kCtas)), dim3(Sh::kThreads), smem, st>>>(
-      mat, evals, evecs, iters, n, batch, layout == JPD_LAYOUT_SOA ? 1 : 0, sort, sweeps);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  JPD_CK(cudaGetLastError());
-  return JPD_OK;
-}
-
-// ------------------------------------------------------------------ tier 5 plan + launch
-BlockPlan make_block_plan(int n, int elem, int calc, int smem_limit) {
-  BlockPlan p{};
-  const int m = n + (n & 1), half = m / 2;
-  p.ldm = n | 1;
-  const size_t base = (size_t)(2 * half + n) * elem + (size_t)(n + 4) * sizeof(int) + 16;
-  const size_t mb = (size_t)n * p.ldm * elem;
-  const size_t eb = calc ? (size_t)n * n * elem : 0;
-  if (base + mb + eb <= (size_t)smem_limit) { p.m_in_smem = 1; p.e_in_smem = 1; }
-  else if (base + mb <= (size_t)smem_limit) { p.m_in_smem = 1; p.e_in_smem = 0; }
-  else { p.m_in_smem = 0; p.e_in_smem = 0; }
-  p.smem_bytes = base + (p.m_in_smem ? mb : 0) + (p.e_in_smem ? eb : 0);
-  p.work_elems = (p.m_in_smem ? 0 : (size_t)n * p.ldm) + ((p.e_in_smem || !calc) ? 0 : (size_t)n * n);
-  const long long items = (long long)half * (half - 1) / 2 + (calc ? (long long)half * n : 0);
-  long long thr = ((items / 4) + 31) / 32 * 32;
-  p.threads = (int)std::min<long long>(1024, std::max<long long>(32, thr));
-  return p;
-}
-
-template <typename T>
-int launch_block(const T* mat, T* evals, T* evecs, int* iters, int n, long long batch, int layout,
-                 int sort, int calc, int sweeps, cudaStream_t st) {
-  int dev = 0;
-  JPD_CK(cudaGetDevice(&dev));
-  DeviceInfo info;
-  int rc = device_info(dev, &info);
-  if (rc != JPD_OK) return rc;
-  const BlockPlan plan = make_block_plan(n, (int)sizeof(T), calc, info.smem_optin);
-  auto kernel = jpd_block_kernel<T>;
-  if (plan.smem_bytes > 48 * 1024)
-    JPD_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
-  int per_sm = 1;
-  JPD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, plan.threads, plan.smem_bytes));
-  if (per_sm < 1) return JPD_ERR_UNSUPPORTED;
-  const long long resident = (long long)per_sm * info.sm_count;
-  const long long grid = std::min<long long>(batch, resident);
-
-  T* work = nullptr;
-  if (plan.work_elems) {
-    {
-      std::lock_guard<std::mutex> lock(g_dev_mutex);
-      if (!g_dev[dev].pool_tuned) {  // keep freed workspace cached in the stream-ordered pool
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-          unsigned long long keep = ~0ull;
-          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        g_dev[dev].pool_tuned = true;
-      }
-    }
-    JPD_CK(cudaMallocAsync((void**)&work, plan.work_elems * sizeof(T) * (size_t)grid, st));
-  }
-  kernel<<<dim3((unsigned)grid), dim3(plan.threads), plan.smem_bytes, st>>>(
-      mat, evals, evecs, iters, n, batch, layout == JPD_LAYOUT_SOA ? 1 : 0, sort, calc, sweeps,
-      plan.ldm, plan.m_in_smem, plan.e_in_smem, work, plan.work_elems);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  cudaError_t le = cudaGetLastError();
-  if (work) cudaFreeAsync(work, st);
-  JPD_CK(le);
-  return JPD_OK;
-}
+using namespace jpd_host;
 
 // ------------------------------------------------------------------ device entry
 template <typename T>
@@ -244,87 +76,11 @@ int diagonalize_device(const T* mat, T* evals, T* evecs, int* iters, int n, long
   if (!mat || !evals || (calc && !evecs)) return JPD_ERR_INVALID_ARG;
   if (sweeps < 0) sweeps = 0;
   calc = calc ? 1 : 0;
-  switch (n) {
-#ifndef JPD_VARIANT_BUILD
-    case 1: return launch_small<1, T>(mat, evals, evecs, iters, batch, layout, sort, calc, sweeps, st);
-    case 2: return launch_small<2, T>(mat, evals, evecs, iters, batch, layout, sort, calc, sweeps, st);
-#endif
-    case 3: return launch_small<3, T>(mat, evals, evecs, iters, batch, layout, sort, calc, sweeps, st);
-    case 4: return launch_small<4, T>(mat, evals, evecs, iters, batch, layout, sort, calc, sweeps, st);
-#ifndef JPD_VARIANT_BUILD
-    case 5: return launch_small<5, T>(mat, evals, evecs, iters, batch, layout, sort, calc, sweeps, st);
-    case 6: return launch_small<6, T>(mat, evals, evecs, iters, batch, layout, sort, calc, sweeps, st);
-#endif
-    default: break;
-  }
-  static_assert(kSmallMaxN == 6, "switch above lists the tier-1 sizes");
-  if (n <= 8) return launch_warp<T, 8>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
-  if (n <= 16) return launch_warp<T, 16>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
-  if (n <= kWarpMaxN) return launch_warp<T, 32>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
-  if (n <= 64) return launch_cta<T, 64>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
-  if (n <= 96) return launch_cta<T, 96>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
-  if (n <= kCtaMaxN) return launch_cta<T, 128>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
-  if (n <= kClusterMaxN) return launch_cluster<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
-  return launch_block<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
-}
-
-// ------------------------------------------------------------------ fused producers
-template <typename T>
-int quaternion_device(const T* corr, T* lambda, T* quat, int* iters, long long batch, int layout,
-                      int all, int sweeps, cudaStream_t st) {
-  if (batch < 0 || (layout != JPD_LAYOUT_AOS && layout != JPD_LAYOUT_SOA)) return JPD_ERR_INVALID_ARG;
-  if (batch == 0) return JPD_OK;
-  if (!corr || !lambda || !quat) return JPD_ERR_INVALID_ARG;
-  if (sweeps < 0) sweeps = 0;
-  const long long blocks = (batch + kSmallThreads - 1) / kSmallThreads;
-  if (blocks > 0x7fffffffLL) return JPD_ERR_UNSUPPORTED;
-  const dim3 grid((unsigned)blocks), block(kSmallThreads);
-  const bool soa = layout == JPD_LAYOUT_SOA;
-  if (all) {
-    if (soa) jpd_quat_kernel<T, true, true><<<grid, block, 0, st>>>(corr, lambda, quat, iters, batch, sweeps);
-    else     jpd_quat_kernel<T, false, true><<<grid, block, 0, st>>>(corr, lambda, quat, iters, batch, sweeps);
-  } else {
-    if (soa) jpd_quat_kernel<T, true, false><<<grid, block, 0, st>>>(corr, lambda, quat, iters, batch, sweeps);
-    else     jpd_quat_kernel<T, false, false><<<grid, block, 0, st>>>(corr, lambda, quat, iters, batch, sweeps);
-  }
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  JPD_CK(cudaGetLastError());
-  return JPD_OK;
-}
-
-template <typename T>
-int principal_axes_device(const T* inertia6, T* moments, T* axes, int* iters, long long batch,
-                          int layout, int sweeps, cudaStream_t st) {
-  if (batch < 0 || (layout != JPD_LAYOUT_AOS && layout != JPD_LAYOUT_SOA)) return JPD_ERR_INVALID_ARG;
-  if (batch == 0) return JPD_OK;
-  if (!inertia6 || !moments || !axes) return JPD_ERR_INVALID_ARG;
-  if (sweeps < 0) sweeps = 0;
-  const long long blocks = (batch + kSmallThreads - 1) / kSmallThreads;
-  if (blocks > 0x7fffffffLL) return JPD_ERR_UNSUPPORTED;
-  const dim3 grid((unsigned)blocks), block(kSmallThreads);
-  if (layout == JPD_LAYOUT_SOA) jpd_inertia_kernel<T, true><<<grid, block, 0, st>>>(inertia6, moments, axes, iters, batch, sweeps);
-  else                          jpd_inertia_kernel<T, false><<<grid, block, 0, st>>>(inertia6, moments, axes, iters, batch, sweeps);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  JPD_CK(cudaGetLastError());
-  return JPD_OK;
-}
-
-// ------------------------------------------------------------------ layout adapters
-template <typename T>
-int convert_layout(const void* src, int src_layout, T* dst, int dst_layout, int n, long long batch,
-                   cudaStream_t st) {
-  if (n < 1 || n > JPD_MAX_N || batch < 0) return JPD_ERR_INVALID_ARG;
-  if (src_layout < kLayoutAoS || src_layout > kLayoutPointers) return JPD_ERR_INVALID_ARG;
-  if (dst_layout < kLayoutAoS || dst_layout > kLayoutPackedSoA) return JPD_ERR_INVALID_ARG;
-  if (batch == 0) return JPD_OK;
-  if (!src || !dst) return JPD_ERR_INVALID_ARG;
-  const long long bx = (batch + 31) / 32;
-  const long long by = ((long long)n * n + 31) / 32;
-  if (bx > 0x7fffffffLL || by > 65535) return JPD_ERR_UNSUPPORTED;
-  jpd_convert_kernel<T><<<dim3((unsigned)bx, (unsigned)by), dim3(32, 8), 0, st>>>(src, src_layout, dst, dst_layout, n, batch);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  JPD_CK(cudaGetLastError());
-  return JPD_OK;
+  if (n <= kSmallMaxN) return launch_tier1<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
+  if (n <= kWarpMaxN) return launch_tier2<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
+  if (n <= kCtaMaxN) return launch_tier3<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
+  if (n <= kClusterMaxN) return launch_tier4<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
+  return launch_tier5<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
 }
 
 // ------------------------------------------------------------------ host pipeline
@@ -491,82 +247,6 @@ int diagonalize_host_multi(const T* h_mat, T* h_evals, T* h_evecs, int* h_iters,
   return JPD_OK;
 }
 
-// ------------------------------------------------------------------ synthetic inputs
-__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
-  unsigned long long z = x + 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
-__device__ __forceinline__ double u_pm1(unsigned long long seed, unsigned long long b, unsigned long long e) {
-  const unsigned long long z = splitmix64(seed ^ (b * 65536ull + e));
-  return (double)(z >> 11) * 0x1.0p-53 * 2.0 - 1.0;
-}
-
-template <typename T>
-__global__ void jpd_synth_kernel(T* __restrict__ mat, int n, long long batch, int soa, int kind,
-                                 unsigned long long seed, long long b0) {
-  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= batch) return;
-  const unsigned long long gb = (unsigned long long)(b0 + b);
-  auto put = [&](int i, int j, double v) {
-    const size_t e = (size_t)i * n + j;
-    mat[soa ? e * (size_t)batch + (size_t)b : (size_t)b * n * n + e] = (T)v;
-  };
-  if (kind == 1) {  // n == 4 checked by the host wrapper
-    double R[9];
-#pragma unroll
-    for (int e = 0; e < 9; ++e) R[e] = u_pm1(seed, gb, (unsigned long long)e);
-    const double xx = R[0], xy = R[1], xz = R[2], yx = R[3], yy = R[4], yz = R[5], zx = R[6], zy = R[7], zz = R[8];
-    const double s00 = __dadd_rn(__dadd_rn(xx, yy), zz), s01 = __dsub_rn(yz, zy), s02 = __dsub_rn(zx, xz), s03 = __dsub_rn(xy, yx);
-    const double s11 = __dsub_rn(__dsub_rn(xx, yy), zz), s12 = __dadd_rn(xy, yx), s13 = __dadd_rn(zx, xz);
-    const double s22 = __dsub_rn(__dsub_rn(yy, xx), zz), s23 = __dadd_rn(yz, zy);
-    const double s33 = __dsub_rn(__dsub_rn(zz, xx), yy);
-    put(0, 0, s00); put(0, 1, s01); put(0, 2, s02); put(0, 3, s03);
-    put(1, 0, s01); put(1, 1, s11); put(1, 2, s12); put(1, 3, s13);
-    put(2, 0, s02); put(2, 1, s12); put(2, 2, s22); put(2, 3, s23);
-    put(3, 0, s03); put(3, 1, s13); put(3, 2, s23); put(3, 3, s33);
-    return;
-  }
-  for (int i = 0; i < n; ++i)
-    for (int j = i; j < n; ++j) {
-      const double v = u_pm1(seed, gb, (unsigned long long)(i * n + j));
-      put(i, j, v);
-      if (j != i) put(j, i, v);
-    }
-}
-
-template <typename T>
-int fill_synthetic(T* d_mat, int n, long long batch, int layout, int kind, unsigned long long seed,
-                   long long b0, cudaStream_t st) {
-  if (n < 1 || n > 256 || batch < 0 || !d_mat) return JPD_ERR_INVALID_ARG;
-  if (kind != 0 && kind != 1) return JPD_ERR_INVALID_ARG;
-  if (kind == 1 && n != 4) return JPD_ERR_INVALID_ARG;
-  if (layout != JPD_LAYOUT_AOS && layout != JPD_LAYOUT_SOA) return JPD_ERR_INVALID_ARG;
-  if (batch == 0) return JPD_OK;
-  const int threads = 128;
-  const long long blocks = (batch + threads - 1) / threads;
-  jpd_synth_kernel<T><<<dim3((unsigned)blocks), dim3(threads), 0, st>>>(d_mat, n, batch, layout == JPD_LAYOUT_SOA, kind, seed, b0);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  JPD_CK(cudaGetLastError());
-  return JPD_OK;
-}
-
-// ------------------------------------------------------------------ FMA-pipe probe
-// Dependent-chain-free FMA stream: 8 independent accumulators per thread, `iters` rounds.
-// bench.py times it with CUDA events to get the measured FP64 / FP32 FMA peak that the
-// FP-bound rooflines (n >= 16) are quoted against (MEASURED_PEAKS.json has no FP64 figure).
-template <typename T>
-__global__ void jpd_fma_probe_kernel(T* out, int iters, T a, T b) {
-  T x0 = T(threadIdx.x), x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-  for (int i = 0; i < iters; ++i) {
-    x0 = jfma(x0, a, b); x1 = jfma(x1, a, b); x2 = jfma(x2, a, b); x3 = jfma(x3, a, b);
-    x4 = jfma(x4, a, b); x5 = jfma(x5, a, b); x6 = jfma(x6, a, b); x7 = jfma(x7, a, b);
-  }
-  const T r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
-  if (r == T(-12345.678)) out[0] = r;  // never true; keeps the chain alive
-}
-
 }  // namespace
 
 // =================================================================== extern "C"
@@ -656,26 +336,6 @@ void jpd_slice(long long batch, int n_parts, int part, long long* first, long lo
   if (count) *count = c;
 }
 
-int jpd_fill_synthetic_f64(double* d_mat, int n, long long batch, int layout, int kind,
-                           unsigned long long seed, long long b0, void* cuda_stream) {
-  return fill_synthetic<double>(d_mat, n, batch, layout, kind, seed, b0, (cudaStream_t)cuda_stream);
-}
-int jpd_fill_synthetic_f32(float* d_mat, int n, long long batch, int layout, int kind,
-                           unsigned long long seed, long long b0, void* cuda_stream) {
-  return fill_synthetic<float>(d_mat, n, batch, layout, kind, seed, b0, (cudaStream_t)cuda_stream);
-}
-
-long long jpd_fma_probe(int elem_size, int blocks, int threads, int iters, void* d_scratch, void* cuda_stream) {
-  if (blocks < 1 || threads < 32 || threads > 1024 || iters < 1 || !d_scratch) return JPD_ERR_INVALID_ARG;
-  cudaStream_t st = (cudaStream_t)cuda_stream;
-  if (elem_size == 8) jpd_fma_probe_kernel<double><<<blocks, threads, 0, st>>>((double*)d_scratch, iters, 0.999999, 1e-9);
-  else if (elem_size == 4) jpd_fma_probe_kernel<float><<<blocks, threads, 0, st>>>((float*)d_scratch, iters, 0.999999f, 1e-9f);
-  else return JPD_ERR_INVALID_ARG;
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  if (cudaGetLastError() != cudaSuccess) return JPD_ERR_CUDA;
-  return 8LL * iters * blocks * threads;  // FMAs issued
-}
-
 long long jpd_algorithmic_bytes(int n, int elem_size, int calc_evecs) {
   if (n < 1 || elem_size < 1) return -1;
   const long long nn = (long long)n * n;
@@ -688,14 +348,7 @@ int jpd_kernel_tier(int n, int elem_size, int calc_evecs) {
   if (n <= kWarpMaxN) return 2;
   if (n <= kCtaMaxN) return 3;
   if (n <= kClusterMaxN) return 4;
-  int limit = 232448, dev = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess) {
-    DeviceInfo info;
-    if (device_info(dev, &info) == JPD_OK) limit = info.smem_optin;
-  } else {
-    (void)cudaGetLastError();
-  }
-  const BlockPlan p = make_block_plan(n, elem_size, calc_evecs ? 1 : 0, limit);
+  (void)calc_evecs;
   return 5;
 }
 
@@ -736,7 +389,7 @@ const char* jpd_error_string(int code) {
     default: return "unknown error";
   }
 }
-const char* jpd_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+const char* jpd_last_cuda_error(void) { return jpd_host::last_cuda_error_cstr(); }
 int jpd_version(void) { return 100; }
 
 }  // extern "C"

@@ -464,7 +464,7 @@ JPD_HD bool small_sort_positions(const T (&ev)[N], int sort_criteria, int (&pos)
 #define JPD_SMALL_THREADS 128
 #endif
 #ifndef JPD_MINB_N3
-#define JPD_MINB_N3 8
+#define JPD_MINB_N3 10
 #endif
 #ifndef JPD_MINB_N4
 #define JPD_MINB_N4 6
@@ -475,7 +475,52 @@ template <int N, typename T> struct SmallLaunch {
                                                      : (N <= 4 ? 8 : (N == 5 ? 6 : 4));
 };
 
+template <int N, typename T, bool SOA>
+__device__ __forceinline__ const T* small_entry_ptr(const T* __restrict__ mat, long long batch, long long b, int i, int j) {
+  return SOA ? mat + (long long)(i * N + j) * batch + b : mat + b * (N * N) + (i * N + j);
+}
+
+// Epilogue of one matrix: eigenvalues from the diagonal (:207-209), SortRows (:477-508) as a
+// permutation of DESTINATIONS, not data: source row r goes to output row pos[r].  (Moving the
+// rows through selects or a local-memory table costs ~200 more instructions per matrix; the
+// scattered 8-byte stores of one warp still fill whole sectors over the N rows and are merged
+// in L2 -- DRAM traffic stays at the algorithmic 8(N+N^2)+4 bytes, see profiles/.)
+template <int N, typename T, bool SOA, bool EVECS>
+__device__ __forceinline__ void small_emit(const T (&m)[SmallShape<N>::kTri], const T (&e)[EVECS ? N * N : 1], int iters,
+                                           bool live, long long b, long long batch, int sort_criteria,
+                                           T* __restrict__ evals, T* __restrict__ evecs, int* __restrict__ n_iters) {
+  using Sh = SmallShape<N>;
+  T ev[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) ev[i] = m[Sh::tri(i, i)];
+  int pos[N];
+  small_sort_positions<N, T>(ev, sort_criteria, pos);
+  if (!live) return;
+  if (n_iters) n_iters[b] = iters;
+#pragma unroll
+  for (int r = 0; r < N; ++r) {
+    if (SOA) evals[(long long)pos[r] * batch + b] = ev[r];
+    else evals[b * N + pos[r]] = ev[r];
+  }
+  if (EVECS) {
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      T* row = SOA ? evecs + (long long)pos[r] * N * batch + b : evecs + b * (N * N) + pos[r] * N;
+#pragma unroll
+      for (int v = 0; v < N; ++v) {
+        if (SOA) row[(long long)v * batch] = e[r * N + v];
+        else row[v] = e[r * N + v];
+      }
+    }
+  }
+}
+
 // layout 0 (AoS): mat[b*N*N + i*N + j]; layout 1 (SoA-interleaved): mat[(i*N+j)*batch + b]
+// One matrix per thread.  (A persistent variant -- warps drawing tiles from a ticket counter,
+// the next tile's entries prefetched into shared memory with cp.async -- was built and measured
+// in round 2: it keeps 5.9 instead of 5.5 warps per scheduler resident and removes the
+// load-latency stalls, and is not faster, because the kernel is bound by the issue port: an
+// FP64 instruction occupies it for two cycles, see DESIGN.md "tier 1".)
 template <int N, typename T, bool SOA, bool EVECS>
 __global__ void __launch_bounds__(JPD_SMALL_THREADS, SmallLaunch<N, T>::kMinBlocks)
 jpd_small_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict__ evecs,
@@ -485,43 +530,14 @@ jpd_small_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = gid < batch;
   const long long b = live ? gid : batch - 1;  // tail lanes shadow the last matrix (no stores)
-
   auto load = [&](T (&m)[Sh::kTri]) {
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
-      for (int j = i; j < N; ++j)
-        m[Sh::tri(i, j)] = SOA ? __ldg(mat + (long long)(i * N + j) * batch + b)
-                               : __ldg(mat + b * (N * N) + (i * N + j));
+      for (int j = i; j < N; ++j) m[Sh::tri(i, j)] = __ldg(small_entry_ptr<N, T, SOA>(mat, batch, b, i, j));
   };
   auto emit = [&](const T (&m)[Sh::kTri], const T (&e)[EVECS ? N * N : 1], int iters) {
-    T ev[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) ev[i] = m[Sh::tri(i, i)];  // :207-209
-    // The sort permutes DESTINATIONS, not data: source row r goes to output row pos[r].  (Moving
-    // the rows through selects or a local-memory table costs ~200 more instructions per matrix;
-    // the scattered 8-byte stores of one warp still fill whole sectors over the N rows and are
-    // merged in L2 -- DRAM traffic stays at the algorithmic 8(N+N^2)+4 bytes, see profiles/.)
-    int pos[N];
-    small_sort_positions<N, T>(ev, sort_criteria, pos);
-    if (!live) return;
-    if (n_iters) n_iters[b] = iters;
-#pragma unroll
-    for (int r = 0; r < N; ++r) {
-      if (SOA) evals[(long long)pos[r] * batch + b] = ev[r];
-      else evals[b * N + pos[r]] = ev[r];
-    }
-    if (EVECS) {
-#pragma unroll
-      for (int r = 0; r < N; ++r) {
-        T* row = SOA ? evecs + (long long)pos[r] * N * batch + b : evecs + b * (N * N) + pos[r] * N;
-#pragma unroll
-        for (int v = 0; v < N; ++v) {
-          if (SOA) row[(long long)v * batch] = e[r * N + v];
-          else row[v] = e[r * N + v];
-        }
-      }
-    }
+    small_emit<N, T, SOA, EVECS>(m, e, iters, live, b, batch, sort_criteria, evals, evecs, n_iters);
   };
   small_solve<N, T, EVECS>(max_num_sweeps, load, emit);
 }

@@ -1,5 +1,7 @@
 #!/bin/bash
-# usage: mkvariant.sh name [extra nvcc -D flags...]
+# usage: mkvariant.sh name [extra nvcc -D flags...]   -> tests/scratch/variants/lib_<name>.so
 name=$1; shift
-/usr/local/cuda/bin/nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xcompiler -pthread -I/root/repo/include -I/root/repo/jacobi_pd_b200/csrc -DJPD_VARIANT_BUILD "$@" -shared -o /root/repo/tests/scratch/variants/lib_$name.so /root/repo/jacobi_pd_b200/csrc/jpd_api.cu 2>&1 | grep -E "error" 
+root=$(cd "$(dirname "$0")/../.." && pwd)
+mkdir -p $root/tests/scratch/variants
+make -C $root/jacobi_pd_b200/csrc OUT=$root/tests/scratch/variants/lib_$name.so OBJ=$root/tests/scratch/variants/obj_$name EXTRA="$*" 2>&1 | grep -E "error|Error"
 echo built $name

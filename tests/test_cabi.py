@@ -1,5 +1,5 @@
 """CPU-only checks of the drop-in boundary: libjpd.so loads, exports every symbol that
-include/jpd.h declares, rejects bad arguments before touching the GPU, and the pure host
+include/jpd.h (product ABI) and include/jpd_bench.h (bench/test scaffolding) declare, rejects bad arguments before touching the GPU, and the pure host
 helpers (slicing, byte model, tier choice) behave.  No compute call is made here."""
 import ctypes
 import os
@@ -13,9 +13,11 @@ from jacobi_pd_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    with open(os.path.join(ROOT, "include", "jpd.h")) as f:
-        text = f.read()
+def declared_symbols(headers=("jpd.h", "jpd_bench.h")):
+    text = ""
+    for h in headers:
+        with open(os.path.join(ROOT, "include", h)) as f:
+            text += f.read()
     return sorted(set(re.findall(r"JPD_API\s+[\w\s\*]+?\b(jpd_\w+)\s*\(", text)))
 
 
@@ -29,7 +31,9 @@ def test_every_declared_symbol_is_exported_and_bound():
     handle = ctypes.CDLL(jpd.LIB_PATH)
     for s in syms:
         assert getattr(handle, s) is not None
-    assert sorted(_lib.SIGNATURES) == syms      # the Python binding covers exactly the header
+    assert sorted(_lib.SIGNATURES) == syms      # the Python binding covers exactly the headers
+    # the product header carries no bench scaffolding
+    assert not [s for s in declared_symbols(("jpd.h",)) if "synthetic" in s or "probe" in s]
 
 
 def test_header_cites_the_reference_interface():
