@@ -20,10 +20,12 @@
 //    of the quad writes it into CTA k (triple-buffered by step).
 //  * Barriers: measured on B200, barrier.cluster arrive.release/wait.acquire costs 443 cycles
 //    (a MEMBAR.ALL.GPU per warp), the relaxed form 106, __syncthreads 45.  The inner loop
-//    therefore uses relaxed cluster barriers, with fence.acq_rel.cluster only in the threads
-//    that wrote another CTA's memory, 3 per A/B step pair (the barrier after a pattern-A block
-//    phase is block-local), and runs a step's eigenvector phase during the NEXT step's pivot
-//    phase (between arrive and wait of its first barrier).
+//    therefore uses relaxed arrives and spells the release out as fence.acq_rel.cluster in the
+//    threads that wrote another CTA's memory plus, where a neighbour will read this CTA's own
+//    rows, ONE cumulative fence per CTA after the block barrier (cluster_arrive_light); 3 cluster
+//    barriers per A/B step pair (the barrier after a pattern-A block phase is block-local); a
+//    step's eigenvector phase runs during the NEXT step's pivot phase (between arrive and wait
+//    of its first barrier).
 // Same odd-even ordering, skip test, rotation, convergence rule and return value.
 #pragma once
 #include "jpd_common.cuh"
@@ -77,17 +79,25 @@ __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_barrier() { cluster_arrive(); cluster_wait(); }
 // Light cluster barrier for the inner loop.  barrier.cluster.arrive.release costs every warp a
-// MEMBAR.ALL.GPU (r1 profile: membar + barrier = 3 stalled warps per issue).  Only threads
-// that wrote ANOTHER CTA's shared memory since the last barrier need that fence; writes to
-// the CTA's own shared memory are ordered by the block barrier and are then visible to any
-// later reader, local or remote (shared memory has one copy).
+// MEMBAR.ALL.GPU (r1 profile: membar + barrier = 3 stalled warps per issue), so the release is
+// spelled out as fences in the threads that need one:
+//  * a thread that wrote ANOTHER CTA's shared memory since the last barrier fences its own
+//    stores (wrote_remote);
+//  * if another CTA will READ, after this barrier, shared memory of THIS CTA that was written
+//    with plain local stores (publish_local: rows of M that pattern B reaches through
+//    ld.shared::cluster, the diagonal read by a neighbour's pivot, the convergence test),
+//    one thread fences AFTER the block barrier: fence.acq_rel.cluster is cumulative, so it
+//    covers every store of the CTA that the block barrier ordered before it, and that
+//    thread's (relaxed) arrive is then the release the readers' wait.acquire pairs with.
+// barrier.cluster.wait is an acquire by default (PTX ISA: .acquire is assumed when absent).
 __device__ __forceinline__ void cluster_fence() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
-__device__ __forceinline__ void cluster_arrive_light(bool wrote_remote) {
+__device__ __forceinline__ void cluster_arrive_light(bool wrote_remote, bool publish_local) {
   if (wrote_remote) cluster_fence();
   __syncthreads();
+  if (publish_local && threadIdx.x == 0) cluster_fence();
   asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void cluster_wait_light() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_light() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ double ld_cluster(unsigned a, double) {
   double v; asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v;
 }
@@ -276,8 +286,12 @@ __device__ __forceinline__ bool cluster_blocks(const ClusterCtx<T>& cx, int buf)
 
 // ---- phase 2b: eigenvector rows of a step of pattern OFF (registers; reads only (c,s) and,
 // for pattern B, the two rows received from the neighbouring chunks)
+// recv_above / recv_below: the rows received from the neighbouring chunks (pattern B only),
+// read by the caller BEFORE it arrives at the cluster barrier that lets the neighbours run
+// ahead and push the next pair of rows (cluster_recv_rows).
 template <typename T, int OFF>
-__device__ __forceinline__ void cluster_evecs(const ClusterCtx<T>& cx, int buf, T (&e)[32]) {
+__device__ __forceinline__ void cluster_evecs(const ClusterCtx<T>& cx, int buf, T (&e)[32],
+                                              T recv_above = T(0), T recv_below = T(0)) {
   using Sh = ClusterShape;
   const int npr = (cx.m >> 1) - OFF;
   const int g = 2 * cx.rank + cx.chl;
@@ -288,11 +302,11 @@ __device__ __forceinline__ void cluster_evecs(const ClusterCtx<T>& cx, int buf, 
   if (OFF == 1) {
     if (g > 0 && j0 - 1 < npr) {
       const T rc = cc[j0 - 1], rs = ss[j0 - 1];
-      new_lo = jfma(rc, cx.from_above[cx.chl * Sh::kN + cx.v], -(rs * e[0]));
+      new_lo = jfma(rc, recv_above, -(rs * e[0]));
     }
     if (g < 7 && j0 + 15 < npr) {
       const T rc = cc[j0 + 15], rs = ss[j0 + 15];
-      new_hi = jfma(rs, e[31], rc * cx.from_below[cx.chl * Sh::kN + cx.v]);
+      new_hi = jfma(rs, e[31], rc * recv_below);
     }
   }
 #pragma unroll
@@ -326,6 +340,12 @@ __device__ __forceinline__ bool cluster_push_rows(const ClusterCtx<T>& cx, const
   return remote;
 }
 
+template <typename T>
+__device__ __forceinline__ void cluster_recv_rows(const ClusterCtx<T>& cx, T& recv_above, T& recv_below) {
+  recv_above = cx.from_above[cx.chl * ClusterShape::kN + cx.v];
+  recv_below = cx.from_below[cx.chl * ClusterShape::kN + cx.v];
+}
+
 // One A step + one B step.  The eigenvector phase of a step is deferred to the NEXT step and
 // runs between arrive and wait of that step's first cluster barrier, i.e. while the pivot
 // warps compute and publish the next rotations (the longest serial stretch of a step).
@@ -333,23 +353,28 @@ __device__ __forceinline__ bool cluster_push_rows(const ClusterCtx<T>& cx, const
 //   B: pivot_B | arrive | E(this A), push boundary rows | wait | blocks_B | cluster barrier
 template <typename T, bool EVECS>
 __device__ __forceinline__ void cluster_step_pair(const ClusterCtx<T>& cx, T (&e)[EVECS ? 32 : 1],
-                                                  bool have_prev, int& buf, int& n_rot) {
+                                                  bool have_prev, bool last_of_sweep, int& buf, int& n_rot) {
   const int buf_prev = buf == 0 ? 2 : buf - 1;          // previous B step
   const int buf_a = buf, buf_b = buf == 2 ? 0 : buf + 1;
   bool wr = cluster_pivot<T, 0>(cx, buf_a, n_rot);
-  cluster_arrive_light(wr);
-  if constexpr (EVECS) { if (have_prev) cluster_evecs<T, 1>(cx, buf_prev, e); }
+  // The rows pushed during the previous B step are taken out of the receive buffers BEFORE the
+  // arrive: a neighbour that runs ahead overwrites them (cluster_push_rows of THIS pair) only
+  // after it has passed this barrier, i.e. after every CTA has read them.
+  T recv_above = T(0), recv_below = T(0);
+  if constexpr (EVECS) { if (have_prev) cluster_recv_rows<T>(cx, recv_above, recv_below); }
+  cluster_arrive_light(wr, true);    // pivot_B of a neighbour reads this CTA's diagonal
+  if constexpr (EVECS) { if (have_prev) cluster_evecs<T, 1>(cx, buf_prev, e, recv_above, recv_below); }
   cluster_wait_light();
   cluster_blocks<T, 0>(cx, buf_a);
   __syncthreads();
 
   wr = cluster_pivot<T, 1>(cx, buf_b, n_rot);
-  cluster_arrive_light(wr);
+  cluster_arrive_light(wr, true);    // blocks_B of a neighbour reads rows this CTA wrote in blocks_A
   wr = false;
   if constexpr (EVECS) { cluster_evecs<T, 0>(cx, buf_a, e); wr = cluster_push_rows<T>(cx, e); }
   cluster_wait_light();
   wr = cluster_blocks<T, 1>(cx, buf_b) || wr;
-  cluster_arrive_light(wr);
+  cluster_arrive_light(wr, last_of_sweep);   // the convergence test reads every CTA's rows
   cluster_wait_light();
   buf = buf_b == 2 ? 0 : buf_b + 1;
 }
@@ -430,12 +455,16 @@ jpd_cluster_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restri
       }
       const int cta_need = __syncthreads_or(mine);
       if (tid < 4) st_cluster_i32(cluster_map(sp.flags + (unsigned)(rank * 4), (unsigned)tid), cta_need);
-      cluster_arrive_light(tid < 4);
+      cluster_arrive_light(tid < 4, false);
       cluster_wait_light();
       need = (flags[0] | flags[1] | flags[2] | flags[3]) != 0;
       if (!need || sweeps >= max_num_sweeps) break;
-      for (int step = 0; step < m; step += 2) cluster_step_pair<T, EVECS>(cx, e, step > 0, buf, n_rot);
-      if constexpr (EVECS) cluster_evecs<T, 1>(cx, buf == 0 ? 2 : buf - 1, e);   // the last B step's eigenvector phase
+      for (int step = 0; step < m; step += 2) cluster_step_pair<T, EVECS>(cx, e, step > 0, step + 2 >= m, buf, n_rot);
+      if constexpr (EVECS) {   // the last B step's eigenvector phase (no push can follow before the next vote)
+        T recv_above, recv_below;
+        cluster_recv_rows<T>(cx, recv_above, recv_below);
+        cluster_evecs<T, 1>(cx, buf == 0 ? 2 : buf - 1, e, recv_above, recv_below);
+      }
       ++sweeps;
     }
     const bool converged = !need && max_num_sweeps > 0;
