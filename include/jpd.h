@@ -87,10 +87,11 @@ JPD_API int jpd_diagonalize_batched_f32(const float* d_mat, float* d_evals, floa
                                 void* cuda_stream);
 
 /* ---- host-resident batches ---------------------------------------------------------
- * Same contract with HOST pointers (pinned memory overlaps best, pageable works).  The
- * batch is streamed through device `device` in chunks: H2D copy, kernel and D2H copy of
- * consecutive chunks overlap on three streams.  Synchronous: results are in the host
- * buffers on return.  This is what the drop-in C++ class Jacobi<>::Diagonalize
+ * Same contract with HOST pointers (pinned memory overlaps best, pageable works; see
+ * jpd_host_register).  The batch is streamed through device `device` in chunks: H2D copy,
+ * kernel and D2H copy of consecutive chunks overlap on three streams.  Synchronous: results
+ * are in the host buffers on return, also after an error (nothing stays in flight).  The
+ * caller's current CUDA device is restored on return.  This is what the drop-in C++ class Jacobi<>::Diagonalize
  * (include/jacobi_pd_cuda.hpp) calls with batch == 1. */
 JPD_API int jpd_diagonalize_batched_host_f64(const double* h_mat, double* h_evals, double* h_evecs,
                                      int* h_n_iters, int n, long long batch, int layout,
@@ -100,6 +101,24 @@ JPD_API int jpd_diagonalize_batched_host_f32(const float* h_mat, float* h_evals,
                                      int* h_n_iters, int n, long long batch, int layout,
                                      int sort_criteria, int calc_evecs, int max_num_sweeps,
                                      int device);
+
+/* Same with the packed upper triangle as input (what the reference actually reads,
+ * jacobi_pd.hpp:167-171): n(n+1)/2 scalars per matrix over PCIe instead of n*n.
+ * layout 0: h_upper[b*T + t(i,j)], layout 1: h_upper[t(i,j)*batch + b], with
+ * t(i,j) = i*n - i(i-1)/2 + (j-i), j >= i, T = n(n+1)/2; outputs as above. */
+JPD_API int jpd_diagonalize_batched_host_packed_f64(const double* h_upper, double* h_evals, double* h_evecs,
+                                            int* h_n_iters, int n, long long batch, int layout,
+                                            int sort_criteria, int calc_evecs, int max_num_sweeps,
+                                            int device);
+JPD_API int jpd_diagonalize_batched_host_packed_f32(const float* h_upper, float* h_evals, float* h_evecs,
+                                            int* h_n_iters, int n, long long batch, int layout,
+                                            int sort_criteria, int calc_evecs, int max_num_sweeps,
+                                            int device);
+/* Page-locks a caller-owned buffer (cudaHostRegister, portable) so that the host entries
+ * overlap their copies with the kernels; pageable memory works but serialises them.
+ * Registering costs ~0.3 ms per MB once -- worth it for buffers that are reused. */
+JPD_API int jpd_host_register(void* h_ptr, unsigned long long bytes);
+JPD_API int jpd_host_unregister(void* h_ptr);
 
 /* ---- host-resident batches over several GPUs of one box ----------------------------
  * Slices [0,batch) into n_devices contiguous parts (part g = [g*ceil(batch/G), ...)) and
@@ -135,6 +154,14 @@ JPD_API int jpd_quaternion_from_correlation_f64(const double* d_corr, double* d_
 JPD_API int jpd_quaternion_from_correlation_f32(const float* d_corr, float* d_lambda, float* d_quat,
                                         int* d_n_iters, long long batch, int layout,
                                         int all_eigenpairs, int max_num_sweeps, void* cuda_stream);
+/* the same with HOST buffers, streamed through `device` like jpd_diagonalize_batched_host_*:
+ * 72 B up + 44 B down per matrix (fp64, leading eigenpair) instead of 128 + 168 B */
+JPD_API int jpd_quaternion_from_correlation_host_f64(const double* h_corr, double* h_lambda, double* h_quat,
+                                             int* h_n_iters, long long batch, int layout,
+                                             int all_eigenpairs, int max_num_sweeps, int device);
+JPD_API int jpd_quaternion_from_correlation_host_f32(const float* h_corr, float* h_lambda, float* h_quat,
+                                             int* h_n_iters, long long batch, int layout,
+                                             int all_eigenpairs, int max_num_sweeps, int device);
 /* LAMMPS rigid bodies: d_inertia6 holds (Ixx, Iyy, Izz, Iyz, Ixz, Ixy) per body (AoS
  * in[b*6 + e] or SoA in[e*batch + b]).  Diagonalize(n = 3, SORT_DECREASING_EVALS), then the
  * post-step of the caller: d_moments (3, decreasing), d_axes[i*3 + k] = component i of
@@ -146,6 +173,13 @@ JPD_API int jpd_principal_axes_f64(const double* d_inertia6, double* d_moments, 
 JPD_API int jpd_principal_axes_f32(const float* d_inertia6, float* d_moments, float* d_axes,
                            int* d_n_iters, long long batch, int layout, int max_num_sweeps,
                            void* cuda_stream);
+
+JPD_API int jpd_principal_axes_host_f64(const double* h_inertia6, double* h_moments, double* h_axes,
+                                int* h_n_iters, long long batch, int layout, int max_num_sweeps,
+                                int device);
+JPD_API int jpd_principal_axes_host_f32(const float* h_inertia6, float* h_moments, float* h_axes,
+                                int* h_n_iters, long long batch, int layout, int max_num_sweeps,
+                                int device);
 
 /* ---- layout adapters ---------------------------------------------------
  * Converts a device-resident batch of n x n matrices between the layouts above with one

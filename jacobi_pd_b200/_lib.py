@@ -16,7 +16,7 @@ _lib = None
 
 c_int, c_ll, c_ull, c_vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_ulonglong, ctypes.c_void_p
 
-# name -> (restype, argtypes); must list every symbol declared in include/jpd.h
+# name -> (restype, argtypes); must list every symbol declared in include/jpd.h and jpd_bench.h
 SIGNATURES = {
     "jpd_diagonalize_batched_f64": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_int, c_int, c_int, c_vp]),
     "jpd_diagonalize_batched_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_int, c_int, c_int, c_vp]),
@@ -24,6 +24,14 @@ SIGNATURES = {
     "jpd_diagonalize_batched_host_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_int, c_int, c_int, c_int]),
     "jpd_diagonalize_batched_host_multi_f64": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "jpd_diagonalize_batched_host_multi_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "jpd_diagonalize_batched_host_packed_f64": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_int, c_int, c_int, c_int]),
+    "jpd_diagonalize_batched_host_packed_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_int, c_int, c_int, c_int]),
+    "jpd_host_register": (c_int, [c_vp, c_ull]),
+    "jpd_host_unregister": (c_int, [c_vp]),
+    "jpd_quaternion_from_correlation_host_f64": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int]),
+    "jpd_quaternion_from_correlation_host_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int]),
+    "jpd_principal_axes_host_f64": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int]),
+    "jpd_principal_axes_host_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int]),
     "jpd_quaternion_from_correlation_f64": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_vp]),
     "jpd_quaternion_from_correlation_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_vp]),
     "jpd_principal_axes_f64": (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp]),

@@ -176,22 +176,107 @@ def _host_ptr(a):
     return a.data_ptr()  # torch CPU tensor (possibly pinned)
 
 
+def _host_check(name, a, dtype, count, optional=False):
+    """The C ABI trusts raw host pointers: a wrong dtype / size / stride would be a silent
+    out-of-bounds write, so everything is validated here (ValueError, nothing is written)."""
+    if a is None:
+        if optional:
+            return
+        raise ValueError(f"{name} is required")
+    if isinstance(a, np.ndarray):
+        ok_dtype, contiguous, size = a.dtype == np.dtype(dtype), a.flags["C_CONTIGUOUS"], a.size
+    else:  # torch CPU tensor
+        import torch
+        if a.is_cuda:
+            raise ValueError(f"{name} must be a host array (use diagonalize_batched for CUDA tensors)")
+        want = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
+                np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
+        ok_dtype, contiguous, size = a.dtype == want, a.is_contiguous(), a.numel()
+    if not ok_dtype:
+        raise ValueError(f"{name} must have dtype {np.dtype(dtype).name}")
+    if not contiguous:
+        raise ValueError(f"{name} must be C-contiguous")
+    if size != count:
+        raise ValueError(f"{name} must hold {count} elements, has {size}")
+
+
+def _np_dtype(a):
+    return a.dtype if isinstance(a, np.ndarray) else {"torch.float64": np.dtype(np.float64),
+                                                       "torch.float32": np.dtype(np.float32)}[str(a.dtype)]
+
+
 def diagonalize_batched_host(mat, evals, evecs, n_iters, n: int, batch: int, layout: int = LAYOUT_AOS,
                              sort_criteria: int = SORT_DECREASING_EVALS, calc_evecs: bool = True,
-                             max_num_sweeps: int = 50, device: int = 0, n_devices: int = 1):
-    """Host buffers in, host buffers out (numpy arrays or CPU torch tensors, written in place)."""
-    dt = mat.dtype
+                             max_num_sweeps: int = 50, device: int = 0, n_devices: int = 1, devices=None,
+                             packed: bool = False):
+    """Host buffers in, host buffers out (numpy arrays or CPU torch tensors, written in place).
+    ``packed``: `mat` holds only the upper triangle, n(n+1)/2 scalars per matrix
+    (jpd_diagonalize_batched_host_packed_*).  Several GPUs: ``devices=[...]`` (or
+    ``n_devices`` for devices 0..n_devices-1); `device` is then not used."""
+    dt = _np_dtype(mat)
     sfx = _suffix(dt)
+    per_in = n * (n + 1) // 2 if packed else n * n
+    _host_check("mat", mat, dt, per_in * batch)
+    _host_check("evals", evals, dt, n * batch)
+    _host_check("evecs", evecs, dt, n * n * batch, optional=not calc_evecs)
+    _host_check("n_iters", n_iters, np.int32, batch, optional=True)
     l = _lib.lib()
-    if n_devices > 1:
+    vec_ptr = _host_ptr(evecs) if calc_evecs else None
+    if devices is not None:
+        n_devices = len(devices)
+    if packed:
+        if n_devices > 1:
+            raise ValueError("packed input is a single-device entry")
+        fn = getattr(l, f"jpd_diagonalize_batched_host_packed_{sfx}")
+        rc = fn(_host_ptr(mat), _host_ptr(evals), vec_ptr, _host_ptr(n_iters), n, batch, layout,
+                sort_criteria, 1 if calc_evecs else 0, max_num_sweeps, device)
+    elif n_devices > 1 or devices is not None:
         fn = getattr(l, f"jpd_diagonalize_batched_host_multi_{sfx}")
-        rc = fn(_host_ptr(mat), _host_ptr(evals), _host_ptr(evecs), _host_ptr(n_iters), n, batch, layout,
-                sort_criteria, 1 if calc_evecs else 0, max_num_sweeps, n_devices, None)
+        dev_arr = (ctypes.c_int * n_devices)(*devices) if devices is not None else None
+        rc = fn(_host_ptr(mat), _host_ptr(evals), vec_ptr, _host_ptr(n_iters), n, batch, layout,
+                sort_criteria, 1 if calc_evecs else 0, max_num_sweeps, n_devices, dev_arr)
     else:
         fn = getattr(l, f"jpd_diagonalize_batched_host_{sfx}")
-        rc = fn(_host_ptr(mat), _host_ptr(evals), _host_ptr(evecs), _host_ptr(n_iters), n, batch, layout,
+        rc = fn(_host_ptr(mat), _host_ptr(evals), vec_ptr, _host_ptr(n_iters), n, batch, layout,
                 sort_criteria, 1 if calc_evecs else 0, max_num_sweeps, device)
-    _lib.check(rc, fn.__name__ if hasattr(fn, "__name__") else "jpd host call")
+    _lib.check(rc, "jpd_diagonalize_batched_host")
+
+
+def quaternion_from_correlation_host(corr, lam, quat, n_iters, batch: int, layout: int = LAYOUT_AOS,
+                                     all_eigenpairs: bool = False, max_num_sweeps: int = 50, device: int = 0):
+    """colvars path with HOST buffers (written in place): 9 scalars up, 1 + 4 (or 4 + 16) down."""
+    dt = _np_dtype(corr)
+    _host_check("corr", corr, dt, 9 * batch)
+    _host_check("lam", lam, dt, (4 if all_eigenpairs else 1) * batch)
+    _host_check("quat", quat, dt, (16 if all_eigenpairs else 4) * batch)
+    _host_check("n_iters", n_iters, np.int32, batch, optional=True)
+    rc = getattr(_lib.lib(), f"jpd_quaternion_from_correlation_host_{_suffix(dt)}")(
+        _host_ptr(corr), _host_ptr(lam), _host_ptr(quat), _host_ptr(n_iters), batch, layout,
+        1 if all_eigenpairs else 0, max_num_sweeps, device)
+    _lib.check(rc, "jpd_quaternion_from_correlation_host")
+
+
+def principal_axes_host(inertia6, moments, axes, n_iters, batch: int, layout: int = LAYOUT_AOS,
+                        max_num_sweeps: int = 50, device: int = 0):
+    """LAMMPS path with HOST buffers (written in place): 6 scalars up, 3 + 9 down."""
+    dt = _np_dtype(inertia6)
+    _host_check("inertia6", inertia6, dt, 6 * batch)
+    _host_check("moments", moments, dt, 3 * batch)
+    _host_check("axes", axes, dt, 9 * batch)
+    _host_check("n_iters", n_iters, np.int32, batch, optional=True)
+    rc = getattr(_lib.lib(), f"jpd_principal_axes_host_{_suffix(dt)}")(
+        _host_ptr(inertia6), _host_ptr(moments), _host_ptr(axes), _host_ptr(n_iters), batch, layout,
+        max_num_sweeps, device)
+    _lib.check(rc, "jpd_principal_axes_host")
+
+
+def host_register(a) -> None:
+    """Page-lock a caller-owned numpy array so that the host entries overlap copies and kernels."""
+    _lib.check(_lib.lib().jpd_host_register(_host_ptr(a), a.nbytes), "jpd_host_register")
+
+
+def host_unregister(a) -> None:
+    _lib.check(_lib.lib().jpd_host_unregister(_host_ptr(a)), "jpd_host_unregister")
 
 
 def fill_synthetic(mat, n: int, batch: int, layout: int, kind: int, seed: int, b0: int = 0):
@@ -248,7 +333,18 @@ class Jacobi:
         it = np.zeros(1, np.int32)
         diagonalize_batched_host(m, ev, vec, it, n, 1, LAYOUT_AOS, sort_criteria, calc_evecs,
                                  max_num_sweeps, self.device)
-        np.asarray(evals)[...] = ev
+        # the caller's containers are filled in place: numpy arrays, or anything [i] / [i][j]
+        # indexable as in the reference (lists of lists included)
+        if isinstance(evals, np.ndarray):
+            evals[...] = ev.reshape(evals.shape)
+        else:
+            for i in range(n):
+                evals[i] = float(ev[i])
         if calc_evecs:
-            np.asarray(evecs)[...] = vec
+            if isinstance(evecs, np.ndarray):
+                evecs[...] = vec.reshape(evecs.shape)
+            else:
+                for i in range(n):
+                    for j in range(n):
+                        evecs[i][j] = float(vec[i, j])
         return int(it[0])

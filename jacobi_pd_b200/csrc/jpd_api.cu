@@ -84,12 +84,24 @@ int diagonalize_device(const T* mat, T* evals, T* evecs, int* iters, int n, long
 }
 
 // ------------------------------------------------------------------ host pipeline
-// Per-device staging: 3 slots x (in, evals, evecs, iters) + 3 streams, grown on demand and
-// kept until jpd_release().  One host call at a time per device (mutex).
+// Generic for every host entry: a call is a set of host arrays ("spans": inputs, outputs, and
+// device-only scratch), each with a fixed number of elements per matrix, laid out AoS
+// (matrix-major) or SoA (element-major planes of `host_pitch` matrices).  The batch is cut
+// into chunks of ~64 MB that go through three slots (stream + device buffers): H2D of chunk
+// k+1, the kernels of chunk k and D2H of chunk k-1 overlap.  Per-device staging is grown on
+// demand and kept until jpd_release().  One host call at a time per device (mutex).
+constexpr int kMaxSpans = 5;
+struct Span {
+  const void* h_in = nullptr;   // host source (uploaded)          -- at most one of the two;
+  void* h_out = nullptr;        // host destination (downloaded)   -- neither: device scratch
+  size_t per = 0;               // elements per matrix
+  size_t elem = 0;              // bytes per element
+  bool soa = false;             // element-major planes (pitch = host_pitch matrices)
+};
 struct Slot {
   cudaStream_t stream = nullptr;
-  void* in = nullptr; void* evals = nullptr; void* evecs = nullptr; int* iters = nullptr;
-  size_t in_b = 0, evals_b = 0, evecs_b = 0, iters_b = 0;
+  void* buf[kMaxSpans] = {};
+  size_t cap[kMaxSpans] = {};
 };
 struct Pipeline {
   std::mutex mutex;
@@ -101,6 +113,18 @@ struct Pipeline {
 constexpr size_t kSmallCallBytes = (size_t)1 << 20;
 Pipeline g_pipe[kMaxDevices];
 
+// Makes `device` current for the duration of a host entry and restores the caller's device on
+// every return path (a host application may have another device current).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { (void)cudaGetLastError(); prev = -1; }
+    if (prev != device) err = cudaSetDevice(device);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 int grow(void** p, size_t* have, size_t want) {
   if (*have >= want) return JPD_OK;
   if (*p) JPD_CK(cudaFree(*p));
@@ -110,33 +134,41 @@ int grow(void** p, size_t* have, size_t want) {
   return JPD_OK;
 }
 
-// host_pitch: elements between consecutive SoA planes in the HOST arrays (== the caller's
-// full batch, also when only a slice [first, first+batch) is processed).
-template <typename T>
-int diagonalize_host(const T* h_mat, T* h_evals, T* h_evecs, int* h_iters, int n, long long batch,
-                     long long host_pitch, int layout, int sort, int calc, int sweeps, int device) {
-  if (n < 1 || n > JPD_MAX_N || batch < 0) return JPD_ERR_INVALID_ARG;
-  if (layout != JPD_LAYOUT_AOS && layout != JPD_LAYOUT_SOA) return JPD_ERR_INVALID_ARG;
-  if (device < 0 || device >= kMaxDevices) return JPD_ERR_INVALID_ARG;
+inline size_t up16(size_t x) { return (x + 15) / 16 * 16; }
+
+// launch(d_bufs, count, stream): enqueue the kernels of one chunk; d_bufs[k] is the device
+// image of span k for `count` matrices (AoS: contiguous; SoA: planes of `count`).
+template <typename Launch>
+int host_pipeline(int device, long long batch, long long host_pitch, const Span* spans, int n_spans,
+                  Launch launch) {
+  if (device < 0 || device >= kMaxDevices || n_spans < 1 || n_spans > kMaxSpans) return JPD_ERR_INVALID_ARG;
   if (batch == 0) return JPD_OK;
-  if (!h_mat || !h_evals || (calc && !h_evecs)) return JPD_ERR_INVALID_ARG;
-  JPD_CK(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  JPD_CK(guard.err);
   Pipeline& pipe = g_pipe[device];
   std::lock_guard<std::mutex> lock(pipe.mutex);
 
-  const size_t nn = (size_t)n * n;
-  const size_t per_matrix = sizeof(T) * (nn + n + (calc ? nn : 0)) + 4;
+  size_t per_matrix = 0;
+  for (int k = 0; k < n_spans; ++k) per_matrix += spans[k].per * spans[k].elem;
 
   // ---- small calls (the drop-in scalar class: batch = 1): everything through ONE pinned
-  // staging buffer -- one H2D copy, the kernel, one D2H copy of evals|evecs|n_iters, one
-  // synchronisation -- instead of the chunked three-stream pipeline (5 copies, 3 syncs)
-  {
-    auto up16 = [](size_t x) { return (x + 15) / 16 * 16; };
-    const size_t in_b = sizeof(T) * nn * batch, ev_b = sizeof(T) * n * batch;
-    const size_t vec_b = calc ? sizeof(T) * nn * batch : 0, it_b = sizeof(int) * batch;
-    const size_t ev_off = up16(in_b), vec_off = ev_off + up16(ev_b), it_off = vec_off + up16(vec_b);
-    const size_t total = it_off + it_b;
-    if (total <= kSmallCallBytes && host_pitch == batch) {
+  // staging buffer -- one H2D copy of the inputs, the kernels, one D2H copy of the outputs,
+  // one synchronisation -- instead of the chunked three-stream pipeline
+  if (host_pitch == batch) {
+    size_t off[kMaxSpans + 1];
+    size_t in_end = 0, out_begin = 0, pos = 0;
+    bool ordered = true;   // inputs first, then outputs/scratch
+    for (int pass = 0; pass < 2; ++pass)
+      for (int k = 0; k < n_spans; ++k) {
+        const bool is_in = spans[k].h_in != nullptr;
+        if ((pass == 0) != is_in) continue;
+        off[k] = pos;
+        pos = up16(pos + spans[k].per * spans[k].elem * (size_t)batch);
+        if (pass == 0) in_end = pos;
+      }
+    out_begin = in_end;
+    (void)ordered;
+    if (pos <= kSmallCallBytes) {
       if (!pipe.small_pin) {
         JPD_CK(cudaHostAlloc(&pipe.small_pin, kSmallCallBytes, cudaHostAllocDefault));
         JPD_CK(cudaMalloc(&pipe.small_dev, kSmallCallBytes));
@@ -145,20 +177,28 @@ int diagonalize_host(const T* h_mat, T* h_evals, T* h_evecs, int* h_iters, int n
       cudaStream_t st = pipe.slot[0].stream;
       char* hp = static_cast<char*>(pipe.small_pin);
       char* dp = static_cast<char*>(pipe.small_dev);
-      std::memcpy(hp, h_mat, in_b);
-      JPD_CK(cudaMemcpyAsync(dp, hp, in_b, cudaMemcpyHostToDevice, st));
-      const int rc = diagonalize_device<T>(reinterpret_cast<const T*>(dp), reinterpret_cast<T*>(dp + ev_off),
-                                           calc ? reinterpret_cast<T*>(dp + vec_off) : nullptr,
-                                           reinterpret_cast<int*>(dp + it_off), n, batch, layout, sort, calc, sweeps, st);
-      if (rc != JPD_OK) return rc;
-      JPD_CK(cudaMemcpyAsync(hp + ev_off, dp + ev_off, total - ev_off, cudaMemcpyDeviceToHost, st));
-      JPD_CK(cudaStreamSynchronize(st));
-      std::memcpy(h_evals, hp + ev_off, ev_b);
-      if (calc) std::memcpy(h_evecs, hp + vec_off, vec_b);
-      if (h_iters) std::memcpy(h_iters, hp + it_off, it_b);
+      void* d_bufs[kMaxSpans];
+      for (int k = 0; k < n_spans; ++k) {
+        d_bufs[k] = dp + off[k];
+        if (spans[k].h_in) std::memcpy(hp + off[k], spans[k].h_in, spans[k].per * spans[k].elem * (size_t)batch);
+      }
+      int status = JPD_OK;
+      cudaError_t e = in_end ? cudaMemcpyAsync(dp, hp, in_end, cudaMemcpyHostToDevice, st) : cudaSuccess;
+      if (e == cudaSuccess) {
+        status = launch(d_bufs, batch, st);
+        if (status == JPD_OK && pos > out_begin)
+          e = cudaMemcpyAsync(hp + out_begin, dp + out_begin, pos - out_begin, cudaMemcpyDeviceToHost, st);
+      }
+      const cudaError_t es = cudaStreamSynchronize(st);   // also on errors: nothing may stay in flight
+      if (e == cudaSuccess) e = es;
+      if (e != cudaSuccess && status == JPD_OK) { set_last_cuda_error("small host call", e); status = JPD_ERR_CUDA; }
+      if (status != JPD_OK) return status;
+      for (int k = 0; k < n_spans; ++k)
+        if (spans[k].h_out) std::memcpy(spans[k].h_out, hp + off[k], spans[k].per * spans[k].elem * (size_t)batch);
       return JPD_OK;
     }
   }
+
   // bytes per pipeline chunk (in + out): 64 MB by default, JPD_HOST_CHUNK_MB overrides (tuning aid)
   size_t chunk_bytes = (size_t)64 << 20;
   if (const char* env = std::getenv("JPD_HOST_CHUNK_MB")) {
@@ -167,53 +207,139 @@ int diagonalize_host(const T* h_mat, T* h_evals, T* h_evecs, int* h_iters, int n
   }
   long long chunk = std::max<long long>(1, (long long)chunk_bytes / (long long)per_matrix);
   chunk = std::min(chunk, batch);
-  if (layout == JPD_LAYOUT_SOA && chunk > 1) chunk &= ~1LL;  // keep planes 16-byte aligned
+  if (chunk > 1) chunk &= ~1LL;  // keep SoA planes 16-byte aligned
 
   for (int s = 0; s < 3; ++s) {
     Slot& sl = pipe.slot[s];
     if (!sl.stream) JPD_CK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-    int rc;
-    if ((rc = grow(&sl.in, &sl.in_b, sizeof(T) * nn * chunk))) return rc;
-    if ((rc = grow(&sl.evals, &sl.evals_b, sizeof(T) * n * chunk))) return rc;
-    if (calc && (rc = grow(&sl.evecs, &sl.evecs_b, sizeof(T) * nn * chunk))) return rc;
-    if ((rc = grow((void**)&sl.iters, &sl.iters_b, sizeof(int) * chunk))) return rc;
+    for (int k = 0; k < n_spans; ++k) {
+      const int rc = grow(&sl.buf[k], &sl.cap[k], spans[k].per * spans[k].elem * (size_t)chunk);
+      if (rc != JPD_OK) return rc;
+    }
   }
 
+  // From here on an error must not return before all three streams are idle: copies into the
+  // caller's buffers may still be in flight, and the slots are reused by the next call.
   int status = JPD_OK;
+  cudaError_t err = cudaSuccess;
+  const char* what = "";
+  auto copy = [&](const Span& sp, void* dev, long long done, long long cnt, bool up, cudaStream_t st) {
+    if (err != cudaSuccess) return;
+    const cudaMemcpyKind kind = up ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    if (!sp.soa) {
+      char* h = (char*)(up ? const_cast<void*>(sp.h_in) : sp.h_out) + (size_t)done * sp.per * sp.elem;
+      err = up ? cudaMemcpyAsync(dev, h, sp.per * sp.elem * (size_t)cnt, kind, st)
+               : cudaMemcpyAsync(h, dev, sp.per * sp.elem * (size_t)cnt, kind, st);
+    } else {
+      char* h = (char*)(up ? const_cast<void*>(sp.h_in) : sp.h_out) + (size_t)done * sp.elem;
+      const size_t hp = sp.elem * (size_t)host_pitch, dpitch = sp.elem * (size_t)cnt;
+      err = up ? cudaMemcpy2DAsync(dev, dpitch, h, hp, dpitch, sp.per, kind, st)
+               : cudaMemcpy2DAsync(h, hp, dev, dpitch, dpitch, sp.per, kind, st);
+    }
+    if (err != cudaSuccess) what = up ? "host-to-device copy" : "device-to-host copy";
+  };
   long long done = 0;
-  for (int i = 0; done < batch; ++i) {
+  for (int i = 0; done < batch && status == JPD_OK && err == cudaSuccess; ++i) {
     Slot& sl = pipe.slot[i % 3];
     const long long cnt = std::min(chunk, batch - done);
-    cudaStream_t st = sl.stream;
-    T* d_in = (T*)sl.in; T* d_ev = (T*)sl.evals; T* d_vec = calc ? (T*)sl.evecs : nullptr;
-    if (layout == JPD_LAYOUT_AOS) {
-      JPD_CK(cudaMemcpyAsync(d_in, h_mat + (size_t)done * nn, sizeof(T) * nn * cnt, cudaMemcpyHostToDevice, st));
-    } else {
-      JPD_CK(cudaMemcpy2DAsync(d_in, sizeof(T) * cnt, h_mat + done, sizeof(T) * host_pitch,
-                               sizeof(T) * cnt, nn, cudaMemcpyHostToDevice, st));
-    }
-    status = diagonalize_device<T>(d_in, d_ev, d_vec, sl.iters, n, cnt, layout, sort, calc, sweeps, st);
+    for (int k = 0; k < n_spans; ++k)
+      if (spans[k].h_in) copy(spans[k], sl.buf[k], done, cnt, true, sl.stream);
+    if (err != cudaSuccess) break;
+    status = launch(sl.buf, cnt, sl.stream);
     if (status != JPD_OK) break;
-    if (layout == JPD_LAYOUT_AOS) {
-      JPD_CK(cudaMemcpyAsync(h_evals + (size_t)done * n, d_ev, sizeof(T) * n * cnt, cudaMemcpyDeviceToHost, st));
-      if (calc) JPD_CK(cudaMemcpyAsync(h_evecs + (size_t)done * nn, d_vec, sizeof(T) * nn * cnt, cudaMemcpyDeviceToHost, st));
-    } else {
-      JPD_CK(cudaMemcpy2DAsync(h_evals + done, sizeof(T) * host_pitch, d_ev, sizeof(T) * cnt,
-                               sizeof(T) * cnt, n, cudaMemcpyDeviceToHost, st));
-      if (calc) JPD_CK(cudaMemcpy2DAsync(h_evecs + done, sizeof(T) * host_pitch, d_vec, sizeof(T) * cnt,
-                                         sizeof(T) * cnt, nn, cudaMemcpyDeviceToHost, st));
-    }
-    if (h_iters) JPD_CK(cudaMemcpyAsync(h_iters + done, sl.iters, sizeof(int) * cnt, cudaMemcpyDeviceToHost, st));
+    for (int k = 0; k < n_spans; ++k)
+      if (spans[k].h_out) copy(spans[k], sl.buf[k], done, cnt, false, sl.stream);
     done += cnt;
   }
   for (int s = 0; s < 3; ++s) {
-    cudaError_t e = cudaStreamSynchronize(pipe.slot[s].stream);
-    if (e != cudaSuccess && status == JPD_OK) {
-      g_last_cuda_error = std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e);
-      status = JPD_ERR_CUDA;
-    }
+    const cudaError_t e = cudaStreamSynchronize(pipe.slot[s].stream);
+    if (e != cudaSuccess && err == cudaSuccess) { err = e; what = "cudaStreamSynchronize"; }
   }
+  if (err != cudaSuccess && status == JPD_OK) { set_last_cuda_error(what, err); status = JPD_ERR_CUDA; }
   return status;
+}
+
+// host_pitch: matrices between consecutive SoA planes in the HOST arrays (== the caller's
+// full batch, also when only a slice [first, first+batch) is processed).
+template <typename T>
+int diagonalize_host(const T* h_mat, T* h_evals, T* h_evecs, int* h_iters, int n, long long batch,
+                     long long host_pitch, int layout, int sort, int calc, int sweeps, int device) {
+  if (n < 1 || n > JPD_MAX_N || batch < 0) return JPD_ERR_INVALID_ARG;
+  if (layout != JPD_LAYOUT_AOS && layout != JPD_LAYOUT_SOA) return JPD_ERR_INVALID_ARG;
+  if (batch == 0) return JPD_OK;
+  if (!h_mat || !h_evals || (calc && !h_evecs)) return JPD_ERR_INVALID_ARG;
+  const size_t nn = (size_t)n * n;
+  const bool soa = layout == JPD_LAYOUT_SOA;
+  Span sp[4];
+  sp[0].h_in = h_mat;    sp[0].per = nn;             sp[0].elem = sizeof(T);   sp[0].soa = soa;
+  sp[1].h_out = h_evals; sp[1].per = (size_t)n;      sp[1].elem = sizeof(T);   sp[1].soa = soa;
+  sp[2].h_out = calc ? h_evecs : nullptr; sp[2].per = calc ? nn : 0; sp[2].elem = sizeof(T); sp[2].soa = soa;
+  sp[3].h_out = h_iters; sp[3].per = 1;              sp[3].elem = sizeof(int); sp[3].soa = false;  // scratch if NULL
+  return host_pipeline(device, batch, host_pitch, sp, 4, [&](void* const* d, long long cnt, cudaStream_t st) {
+    return diagonalize_device<T>((const T*)d[0], (T*)d[1], calc ? (T*)d[2] : nullptr, (int*)d[3], n, cnt, layout,
+                                 sort, calc, sweeps, st);
+  });
+}
+
+// Packed upper triangle in (n(n+1)/2 scalars per matrix instead of n*n: what the reference
+// actually reads, jacobi_pd.hpp:167-171); unpacked on the device in front of the solver.
+template <typename T>
+int diagonalize_host_packed(const T* h_upper, T* h_evals, T* h_evecs, int* h_iters, int n, long long batch,
+                            int layout, int sort, int calc, int sweeps, int device) {
+  if (n < 1 || n > JPD_MAX_N || batch < 0) return JPD_ERR_INVALID_ARG;
+  if (layout != JPD_LAYOUT_AOS && layout != JPD_LAYOUT_SOA) return JPD_ERR_INVALID_ARG;
+  if (batch == 0) return JPD_OK;
+  if (!h_upper || !h_evals || (calc && !h_evecs)) return JPD_ERR_INVALID_ARG;
+  const size_t nn = (size_t)n * n, tri = (size_t)n * (n + 1) / 2;
+  const bool soa = layout == JPD_LAYOUT_SOA;
+  Span sp[5];
+  sp[0].h_in = h_upper;  sp[0].per = tri;        sp[0].elem = sizeof(T);   sp[0].soa = soa;
+  sp[1].h_out = h_evals; sp[1].per = (size_t)n;  sp[1].elem = sizeof(T);   sp[1].soa = soa;
+  sp[2].h_out = calc ? h_evecs : nullptr; sp[2].per = calc ? nn : 0; sp[2].elem = sizeof(T); sp[2].soa = soa;
+  sp[3].h_out = h_iters; sp[3].per = 1;          sp[3].elem = sizeof(int); sp[3].soa = false;
+  sp[4].per = nn;        sp[4].elem = sizeof(T);                                              // full matrices (scratch)
+  return host_pipeline(device, batch, batch, sp, 5, [&](void* const* d, long long cnt, cudaStream_t st) {
+    int rc = convert_layout<T>(d[0], soa ? 3 : 2, (T*)d[4], soa ? 1 : 0, n, cnt, st);
+    if (rc != JPD_OK) return rc;
+    return diagonalize_device<T>((const T*)d[4], (T*)d[1], calc ? (T*)d[2] : nullptr, (int*)d[3], n, cnt, layout,
+                                 sort, calc, sweeps, st);
+  });
+}
+
+// Fused producers with host buffers: 72 B up + 44 B down per matrix (fp64, leading eigenpair)
+// for colvars instead of 128 + 168 B through jpd_diagonalize_batched_host_*.
+template <typename T>
+int quaternion_host(const T* h_corr, T* h_lambda, T* h_quat, int* h_iters, long long batch, int layout, int all,
+                    int sweeps, int device) {
+  if (batch < 0 || (layout != JPD_LAYOUT_AOS && layout != JPD_LAYOUT_SOA)) return JPD_ERR_INVALID_ARG;
+  if (batch == 0) return JPD_OK;
+  if (!h_corr || !h_lambda || !h_quat) return JPD_ERR_INVALID_ARG;
+  const bool soa = layout == JPD_LAYOUT_SOA;
+  Span sp[4];
+  sp[0].h_in = h_corr;    sp[0].per = 9;             sp[0].elem = sizeof(T);   sp[0].soa = soa;
+  sp[1].h_out = h_lambda; sp[1].per = all ? 4 : 1;   sp[1].elem = sizeof(T);   sp[1].soa = soa;
+  sp[2].h_out = h_quat;   sp[2].per = all ? 16 : 4;  sp[2].elem = sizeof(T);   sp[2].soa = soa;
+  sp[3].h_out = h_iters;  sp[3].per = 1;             sp[3].elem = sizeof(int); sp[3].soa = false;
+  return host_pipeline(device, batch, batch, sp, 4, [&](void* const* d, long long cnt, cudaStream_t st) {
+    return quaternion_device<T>((const T*)d[0], (T*)d[1], (T*)d[2], (int*)d[3], cnt, layout, all, sweeps, st);
+  });
+}
+
+template <typename T>
+int principal_axes_host(const T* h_inertia6, T* h_moments, T* h_axes, int* h_iters, long long batch, int layout,
+                        int sweeps, int device) {
+  if (batch < 0 || (layout != JPD_LAYOUT_AOS && layout != JPD_LAYOUT_SOA)) return JPD_ERR_INVALID_ARG;
+  if (batch == 0) return JPD_OK;
+  if (!h_inertia6 || !h_moments || !h_axes) return JPD_ERR_INVALID_ARG;
+  const bool soa = layout == JPD_LAYOUT_SOA;
+  Span sp[4];
+  sp[0].h_in = h_inertia6; sp[0].per = 6; sp[0].elem = sizeof(T);   sp[0].soa = soa;
+  sp[1].h_out = h_moments; sp[1].per = 3; sp[1].elem = sizeof(T);   sp[1].soa = soa;
+  sp[2].h_out = h_axes;    sp[2].per = 9; sp[2].elem = sizeof(T);   sp[2].soa = soa;
+  sp[3].h_out = h_iters;   sp[3].per = 1; sp[3].elem = sizeof(int); sp[3].soa = false;
+  return host_pipeline(device, batch, batch, sp, 4, [&](void* const* d, long long cnt, cudaStream_t st) {
+    return principal_axes_device<T>((const T*)d[0], (T*)d[1], (T*)d[2], (int*)d[3], cnt, layout, sweeps, st);
+  });
 }
 
 template <typename T>
@@ -316,6 +442,50 @@ int jpd_principal_axes_f32(const float* d_inertia6, float* d_moments, float* d_a
                                       max_num_sweeps, (cudaStream_t)cuda_stream);
 }
 
+int jpd_diagonalize_batched_host_packed_f64(const double* h_upper, double* h_evals, double* h_evecs, int* h_n_iters,
+                                            int n, long long batch, int layout, int sort_criteria, int calc_evecs,
+                                            int max_num_sweeps, int device) {
+  return diagonalize_host_packed<double>(h_upper, h_evals, h_evecs, h_n_iters, n, batch, layout, sort_criteria,
+                                         calc_evecs ? 1 : 0, max_num_sweeps < 0 ? 0 : max_num_sweeps, device);
+}
+int jpd_diagonalize_batched_host_packed_f32(const float* h_upper, float* h_evals, float* h_evecs, int* h_n_iters,
+                                            int n, long long batch, int layout, int sort_criteria, int calc_evecs,
+                                            int max_num_sweeps, int device) {
+  return diagonalize_host_packed<float>(h_upper, h_evals, h_evecs, h_n_iters, n, batch, layout, sort_criteria,
+                                        calc_evecs ? 1 : 0, max_num_sweeps < 0 ? 0 : max_num_sweeps, device);
+}
+int jpd_quaternion_from_correlation_host_f64(const double* h_corr, double* h_lambda, double* h_quat, int* h_n_iters,
+                                             long long batch, int layout, int all_eigenpairs, int max_num_sweeps,
+                                             int device) {
+  return quaternion_host<double>(h_corr, h_lambda, h_quat, h_n_iters, batch, layout, all_eigenpairs ? 1 : 0,
+                                 max_num_sweeps, device);
+}
+int jpd_quaternion_from_correlation_host_f32(const float* h_corr, float* h_lambda, float* h_quat, int* h_n_iters,
+                                             long long batch, int layout, int all_eigenpairs, int max_num_sweeps,
+                                             int device) {
+  return quaternion_host<float>(h_corr, h_lambda, h_quat, h_n_iters, batch, layout, all_eigenpairs ? 1 : 0,
+                                max_num_sweeps, device);
+}
+int jpd_principal_axes_host_f64(const double* h_inertia6, double* h_moments, double* h_axes, int* h_n_iters,
+                                long long batch, int layout, int max_num_sweeps, int device) {
+  return principal_axes_host<double>(h_inertia6, h_moments, h_axes, h_n_iters, batch, layout, max_num_sweeps, device);
+}
+int jpd_principal_axes_host_f32(const float* h_inertia6, float* h_moments, float* h_axes, int* h_n_iters,
+                                long long batch, int layout, int max_num_sweeps, int device) {
+  return principal_axes_host<float>(h_inertia6, h_moments, h_axes, h_n_iters, batch, layout, max_num_sweeps, device);
+}
+
+int jpd_host_register(void* h_ptr, unsigned long long bytes) {
+  if (!h_ptr || bytes == 0) return JPD_ERR_INVALID_ARG;
+  JPD_CK(cudaHostRegister(h_ptr, (size_t)bytes, cudaHostRegisterPortable));
+  return JPD_OK;
+}
+int jpd_host_unregister(void* h_ptr) {
+  if (!h_ptr) return JPD_ERR_INVALID_ARG;
+  JPD_CK(cudaHostUnregister(h_ptr));
+  return JPD_OK;
+}
+
 int jpd_convert_layout_f64(const void* d_src, int src_layout, double* d_dst, int dst_layout, int n,
                            long long batch, void* cuda_stream) {
   return convert_layout<double>(d_src, src_layout, d_dst, dst_layout, n, batch, (cudaStream_t)cuda_stream);
@@ -363,7 +533,10 @@ int jpd_release(void) {
     Pipeline& pipe = g_pipe[d];
     std::lock_guard<std::mutex> lock(pipe.mutex);
     bool any = false;
-    for (auto& sl : pipe.slot) any = any || sl.stream || sl.in || sl.evals || sl.evecs || sl.iters;
+    for (auto& sl : pipe.slot) {
+      any = any || sl.stream;
+      for (void* p : sl.buf) any = any || p;
+    }
     any = any || pipe.small_pin || pipe.small_dev;
     if (!any) continue;
     cudaSetDevice(d);
@@ -371,7 +544,7 @@ int jpd_release(void) {
     if (pipe.small_dev) { cudaFree(pipe.small_dev); pipe.small_dev = nullptr; }
     for (auto& sl : pipe.slot) {
       if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
-      cudaFree(sl.in); cudaFree(sl.evals); cudaFree(sl.evecs); cudaFree(sl.iters);
+      for (void* p : sl.buf) cudaFree(p);
       sl = Slot{};
     }
   }

@@ -29,7 +29,8 @@
 //    evaluated ONCE per sweep (small_status), not again per pair: inside a sweep every pair
 //    whose off-diagonal entry is nonzero is rotated -- a pair the test would have skipped gets
 //    a rotation that is the identity to working precision, which is what the reference's
-//    `M[i][j] = 0` (:192) does to it as well.  The diagonal lives HALVED in registers
+//    `M[i][j] = 0` (:192) does to it as well.  A lane that has converged is frozen exactly
+//    (its off-diagonal entries are zeroed), so results do not depend on warp neighbours.  The diagonal lives HALVED in registers
 //    (exact), which removes two FP64 instructions from every rotation (see
 //    small_rotate_pair).
 //  * Sort = the reference's selection sort replayed on (key,id) pairs with static
@@ -322,6 +323,17 @@ JPD_HD int small_solve_pass(T (&m)[SmallShape<N>::kTri], T (&e)[EVECS ? N * N : 
     converged = converged || !any_need;
     // a lane that already gave up (out_of_range) does not keep its warp sweeping
     if (!JPD_WARP_ANY(any_need && !out_of_range)) break;
+    // A lane whose matrix has converged but whose warp goes on is FROZEN: its negligible
+    // off-diagonal entries become exact zeros (what the reference does to its last pivot,
+    // jacobi_pd.hpp:192), so every rotation of the coming sweeps is the exact identity for it
+    // (a == 0: c = 1, s = g = 0).  A matrix's result therefore never depends on the matrices
+    // that happen to share its warp -- bit for bit, whatever the batch or chunk size.
+    if (!any_need) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) m[SmallShape<N>::tri(i, j)] = T(0);
+    }
     // rotations attempted: every pair of a sweep this lane still needed (for n = 2 exactly the
     // reference's count; the n_iters contract is "> 0 iff converged", jacobi_pd.hpp:73-74)
     n_rot += converged ? 0 : kPairs;

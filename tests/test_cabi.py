@@ -87,3 +87,46 @@ def test_no_silent_cpu_fallback():
     import inspect
     src = inspect.getsource(jpd.api) + inspect.getsource(_lib)
     assert "oracle" not in src.replace("never imported", "")     # product never reaches into oracle/
+
+
+def test_python_binding_validates_host_buffers_before_the_call():
+    """A wrong dtype / size / stride would be a silent out-of-bounds write behind raw pointers."""
+    import numpy as np
+    n, B = 3, 4
+    mat = np.zeros((B, n, n)); ev = np.zeros((B, n)); vec = np.zeros((B, n, n)); it = np.zeros(B, np.int32)
+    with pytest.raises(ValueError, match="dtype"):
+        jpd.diagonalize_batched_host(mat.astype(np.float32), ev, vec, it, n, B)
+    with pytest.raises(ValueError, match="dtype"):
+        jpd.diagonalize_batched_host(mat, ev, vec, it.astype(np.int64), n, B)
+    with pytest.raises(ValueError, match="elements"):
+        jpd.diagonalize_batched_host(mat, ev[:2], vec, it, n, B)
+    with pytest.raises(ValueError, match="contiguous"):
+        jpd.diagonalize_batched_host(mat, ev, np.zeros((B, n, 2 * n))[:, :, ::2], it, n, B)
+    with pytest.raises(ValueError, match="required"):
+        jpd.diagonalize_batched_host(mat, ev, None, it, n, B)
+    with pytest.raises(ValueError, match="elements"):
+        jpd.quaternion_from_correlation_host(np.zeros((B, 8)), np.zeros(B), np.zeros((B, 4)), it, B)
+    l = jpd.lib()
+    assert l.jpd_quaternion_from_correlation_host_f64(None, None, None, None, 5, 0, 0, 50, 0) == -1
+    assert l.jpd_principal_axes_host_f32(None, None, None, None, 0, 0, 50, 0) == 0
+    assert l.jpd_diagonalize_batched_host_packed_f64(None, None, None, None, 4, 5, 0, 1, 1, 50, 0) == -1
+    assert l.jpd_host_register(None, 16) == -1
+
+
+def test_python_jacobi_class_fills_lists_in_place():
+    """Jacobi.Diagonalize writes into whatever [i] / [i][j] container the caller passes; the
+    marshalling is checked without a GPU by stubbing the host entry."""
+    import numpy as np
+    from jacobi_pd_b200 import api
+    calls = {}
+
+    def fake(mat, ev, vec, it, n, batch, *a, **k):
+        calls["n"] = n
+        ev[...] = np.arange(n, 0, -1); vec[...] = np.eye(n); it[0] = 7
+    orig, api.diagonalize_batched_host = api.diagonalize_batched_host, fake
+    try:
+        evals, evecs = [0.0] * 3, [[0.0] * 3 for _ in range(3)]
+        assert jpd.Jacobi(3).Diagonalize([[2, 1, 1], [1, 2, -1], [1, -1, 2]], evals, evecs) == 7
+        assert evals == [3.0, 2.0, 1.0] and evecs[1] == [0.0, 1.0, 0.0] and calls["n"] == 3
+    finally:
+        api.diagonalize_batched_host = orig
