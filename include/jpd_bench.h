@@ -11,6 +11,8 @@ extern "C" {
  * Counter-based generator, identical bits on host and device:
  *   kind 0: upper-triangle entries iid U(-1,1), mirrored
  *   kind 1: n == 4, quaternion-superposition overlap matrix of a 3x3 U(-1,1) correlation
+ *   kind 2: n == 3, that 3x3 correlation matrix itself (row-major, NOT symmetric; device only):
+ *           the input of jpd_quaternion_from_correlation_* whose overlap matrix is kind 1
  * Writes matrices b0 .. b0+batch-1 of the stream at local indices 0..batch-1 (device ptr). */
 JPD_API int jpd_fill_synthetic_f64(double* d_mat, int n, long long batch, int layout, int kind,
                            unsigned long long seed, long long b0, void* cuda_stream);

@@ -31,6 +31,11 @@ __global__ void jpd_synth_kernel(T* __restrict__ mat, int n, long long batch, in
     const size_t e = (size_t)i * n + j;
     mat[soa ? e * (size_t)batch + (size_t)b : (size_t)b * n * n + e] = (T)v;
   };
+  if (kind == 2) {  // n == 3 checked by the host wrapper: the correlation matrix itself (NOT symmetric)
+#pragma unroll
+    for (int e = 0; e < 9; ++e) mat[soa ? (size_t)e * (size_t)batch + (size_t)b : (size_t)b * 9 + e] = (T)u_pm1(seed, gb, (unsigned long long)e);
+    return;
+  }
   if (kind == 1) {  // n == 4 checked by the host wrapper
     double R[9];
 #pragma unroll
@@ -58,8 +63,8 @@ template <typename T>
 int fill_synthetic(T* d_mat, int n, long long batch, int layout, int kind, unsigned long long seed,
                    long long b0, cudaStream_t st) {
   if (n < 1 || n > 256 || batch < 0 || !d_mat) return JPD_ERR_INVALID_ARG;
-  if (kind != 0 && kind != 1) return JPD_ERR_INVALID_ARG;
-  if (kind == 1 && n != 4) return JPD_ERR_INVALID_ARG;
+  if (kind < 0 || kind > 2) return JPD_ERR_INVALID_ARG;
+  if ((kind == 1 && n != 4) || (kind == 2 && n != 3)) return JPD_ERR_INVALID_ARG;
   if (layout != JPD_LAYOUT_AOS && layout != JPD_LAYOUT_SOA) return JPD_ERR_INVALID_ARG;
   if (batch == 0) return JPD_OK;
   const int threads = 128;

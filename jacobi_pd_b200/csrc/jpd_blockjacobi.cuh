@@ -1,0 +1,283 @@
+// jpd_blockjacobi.cuh -- tier 5: block Jacobi for 257 <= n <= 1024 (the reference benchmarks
+// its header up to n = 1000, /root/reference/benchmarks/README.md:19-20).
+//
+// Path being replaced: Jacobi::Diagonalize, /root/reference/include/jacobi_pd.hpp:159-220.
+//
+// A matrix of this size is worked on by the WHOLE device, one outer step at a time:
+//  * The indices are cut into blocks of 32 (the matrix is padded to a multiple of 64 with
+//    decoupled zero rows/columns, which no rotation ever touches: their off-diagonal entries
+//    are exact zeros).  An outer sweep is the round-robin tournament of the block indices:
+//    nb-1 steps, each pairing all blocks into nb/2 disjoint pairs (I,J).
+//  * For every pair the 64 x 64 pivot matrix M[I u J, I u J] is gathered (blk_gather) and
+//    diagonalised by the tier-3 kernel (jpd_cta.cuh: the odd-even two-sided Jacobi with the
+//    reference's skip test :191 and CalcRot :233-256) -- a batch of nb/2 x matrices
+//    independent 64 x 64 problems; its eigenvector rows are the orthogonal block Q.
+//  * ApplyRot / ApplyRotLeft (:327-393, :409-419) for ALL the rotations of those solves at once
+//    are two small GEMMs per 64 x 64 tile: M[R_k, R_l] <- Q_k M[R_k, R_l] Q_l^T and
+//    E[R_k, :] <- Q_k E[R_k, :] (blk_apply), register-tiled FP64 FMA.  A product of the ~4000
+//    rotations of one pivot solve applied as a dense 64 x 64 block costs 64 FMAs per entry
+//    instead of ~250, and every entry of M makes ONE round trip through shared memory per
+//    outer step instead of one per rotation step.
+//  * Convergence: every index pair belongs to exactly one pivot block per sweep, so a sweep
+//    in which no pivot solve performed a rotation is a sweep in which every pair passed the
+//    reference's test -- the same stopping rule as the other tiers.  The host reads one flag
+//    per sweep (the call therefore synchronises its stream once per outer sweep).
+#pragma once
+#include "jpd_common.cuh"
+
+namespace jpd {
+
+constexpr int kBjBlock = 32;          // indices per block
+constexpr int kBjPivot = 64;          // pivot matrix = two blocks
+constexpr int kBjLd = 66;             // shared-memory row pitch (elements): 16-byte aligned rows,
+                                      // rows r and r+4 in different banks
+constexpr int kBjThreads = 256;
+
+#if defined(__CUDACC__)
+
+// ---- workspace initialisation: symmetric padded M from the caller's upper triangle (:167-171), E = I
+template <typename T>
+__global__ void __launch_bounds__(256)
+blk_init_kernel(const T* __restrict__ mat, T* __restrict__ Mw, T* __restrict__ Ew, int n, int np,
+                long long batch, long long b0, long long count, int soa) {
+  const long long total = count * (long long)np * np;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long lb = idx / ((long long)np * np);
+    const int rem = (int)(idx - lb * (long long)np * np);
+    const int r = rem / np, c = rem - r * np;
+    T v = T(0);
+    if (r < n && c < n) {
+      const int i = r < c ? r : c, j = r < c ? c : r;
+      const size_t e = (size_t)i * n + j;
+      const long long b = b0 + lb;
+      v = soa ? mat[e * (size_t)batch + (size_t)b] : mat[(size_t)b * n * n + e];
+    }
+    Mw[idx] = v;
+    Ew[idx] = (r == c) ? T(1) : T(0);
+  }
+}
+
+// rows of pair (I,J): local row q (0..63) -> global row
+__device__ __forceinline__ int bj_row(int I, int J, int q) {
+  return (q < kBjBlock ? I * kBjBlock : J * kBjBlock - kBjBlock) + q;
+}
+
+// ---- pivot matrices of one step: P[(lb * npairs + k)] = M[R_k, R_k], AoS 64 x 64
+template <typename T>
+__global__ void __launch_bounds__(kBjThreads)
+blk_gather_kernel(const T* __restrict__ Mw, T* __restrict__ P, const int2* __restrict__ pairs, int npairs, int np) {
+  const int k = blockIdx.x, lb = blockIdx.y;
+  const int2 pr = pairs[k];
+  const T* M = Mw + (size_t)lb * np * np;
+  T* out = P + ((size_t)lb * npairs + k) * (kBjPivot * kBjPivot);
+  for (int idx = threadIdx.x; idx < kBjPivot * kBjPivot; idx += kBjThreads) {
+    const int r = idx >> 6, c = idx & 63;
+    out[idx] = M[(size_t)bj_row(pr.x, pr.y, r) * np + bj_row(pr.x, pr.y, c)];
+  }
+}
+
+// C(4x4 per thread) += A(rows 4ty.., all l) * B(all l, cols 4tx..); A, B in shared memory, pitch kBjLd
+template <typename T>
+__device__ __forceinline__ void bj_gemm_64(const T* __restrict__ A, const T* __restrict__ B, int ty, int tx, T (&c)[4][4]) {
+#pragma unroll 8
+  for (int l = 0; l < kBjPivot; ++l) {
+    T a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = A[(4 * ty + i) * kBjLd + l];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = B[l * kBjLd + 4 * tx + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[i][j] = jfma(a[i], b[j], c[i][j]);
+  }
+}
+
+// ---- ApplyRot + ApplyRotLeft of one outer step.  Work items (blockIdx.x) per matrix:
+//   [0, ntile)          tile (k <= l) of M:  M[R_k, R_l] <- Q_k M[R_k, R_l] Q_l^T, and its mirror image
+//   [ntile, ntile + npairs * ncol)   (k, col block c) of E:  E[R_k, C_c] <- Q_k E[R_k, C_c]
+// Q_k = eigenvector ROWS of pivot solve k (row a = new index a).
+template <typename T, bool EVECS>
+__global__ void __launch_bounds__(kBjThreads, 2)
+blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q,
+                 const int2* __restrict__ pairs, int npairs, int np) {
+  extern __shared__ __align__(16) unsigned char bj_smem_raw[];
+  T* sQa = reinterpret_cast<T*>(bj_smem_raw);      // Q_k, row-major (A operand)
+  T* sX = sQa + kBjPivot * kBjLd;                    // the tile (B operand), later T = Q_k X (A operand)
+  T* sQbt = sX + kBjPivot * kBjLd;                   // Q_l^T (B operand)
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int lb = blockIdx.y;
+  const int ntile = npairs * (npairs + 1) / 2;
+  const int item = blockIdx.x;
+  T* M = Mw + (size_t)lb * np * np;
+  const T* Qb = Q + (size_t)lb * npairs * (kBjPivot * kBjPivot);
+
+  if (item < ntile) {
+    // (k, l), k <= l, from the linear index
+    int k = 0, rest = item;
+    while (rest >= npairs - k) { rest -= npairs - k; ++k; }
+    const int l = k + rest;
+    const int2 pk = pairs[k], pl = pairs[l];
+    for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjThreads) {
+      const int r = idx >> 6, c = idx & 63;
+      sQa[r * kBjLd + c] = Qb[(size_t)k * 4096 + idx];
+      sQbt[c * kBjLd + r] = Qb[(size_t)l * 4096 + idx];                       // transposed
+      sX[r * kBjLd + c] = M[(size_t)bj_row(pk.x, pk.y, r) * np + bj_row(pl.x, pl.y, c)];
+    }
+    __syncthreads();
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+    bj_gemm_64(sQa, sX, ty, tx, acc);                 // T = Q_k X
+    __syncthreads();                                   // every thread has read X
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { sX[(4 * ty + i) * kBjLd + 4 * tx + j] = acc[i][j]; acc[i][j] = T(0); }
+    __syncthreads();
+    bj_gemm_64(sX, sQbt, ty, tx, acc);                // T Q_l^T
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gr = bj_row(pk.x, pk.y, 4 * ty + i);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gc = bj_row(pl.x, pl.y, 4 * tx + j);
+        M[(size_t)gr * np + gc] = acc[i][j];
+        if (k != l) M[(size_t)gc * np + gr] = acc[i][j];    // the matrix stays symmetric bit for bit
+      }
+    }
+    if (k == l) {
+      // symmetrise the diagonal tile's two triangles (Q P Q^T is symmetric only up to rounding)
+      __syncthreads();
+      for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjThreads) {
+        const int r = idx >> 6, c = idx & 63;
+        if (r > c) {
+          const int gr = bj_row(pk.x, pk.y, r), gc = bj_row(pk.x, pk.y, c);
+          M[(size_t)gr * np + gc] = M[(size_t)gc * np + gr];
+        }
+      }
+    }
+  } else if (EVECS) {
+    const int e_item = item - ntile;
+    const int ncol = np / kBjPivot;
+    const int k = e_item / ncol, cb = e_item - k * ncol;
+    const int2 pk = pairs[k];
+    T* E = Ew + (size_t)lb * np * np;
+    for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjThreads) {
+      const int r = idx >> 6, c = idx & 63;
+      sQa[r * kBjLd + c] = Qb[(size_t)k * 4096 + idx];
+      sX[r * kBjLd + c] = E[(size_t)bj_row(pk.x, pk.y, r) * np + cb * kBjPivot + c];
+    }
+    __syncthreads();
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+    bj_gemm_64(sQa, sX, ty, tx, acc);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gr = bj_row(pk.x, pk.y, 4 * ty + i);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) E[(size_t)gr * np + cb * kBjPivot + 4 * tx + j] = acc[i][j];
+    }
+  }
+}
+
+// ---- bookkeeping of one step: rotations of the pivot solves, per matrix.  piv_iters follows the
+// reference's return value (rotations + 1, or 0 when the inner solve ran out of sweeps).
+__global__ void blk_count_kernel(const int* __restrict__ piv_iters, int npairs, long long count,
+                                 int* __restrict__ rot_total, int* __restrict__ rot_sweep, int* __restrict__ any_left) {
+  const long long lb = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lb >= count) return;
+  int rot = 0;
+  for (int k = 0; k < npairs; ++k) {
+    const int it = piv_iters[lb * npairs + k];
+    rot += it > 0 ? it - 1 : 1 << 16;      // an unfinished inner solve certainly rotated
+  }
+  if (rot) {
+    rot_total[lb] = min(rot_total[lb] + rot, 0x3fffffff);
+    rot_sweep[lb] += 1;
+    *any_left = 1;
+  }
+}
+
+// called between sweeps: remembers which matrices were already done BEFORE the sweep that just ended
+__global__ void blk_sweep_end_kernel(int* __restrict__ rot_sweep, int* __restrict__ converged, long long count) {
+  const long long lb = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lb >= count) return;
+  if (rot_sweep[lb] == 0) converged[lb] = 1;     // a whole sweep without a rotation (:191 on every pair)
+  rot_sweep[lb] = 0;
+}
+
+// ---- eigenvalues (:207-209), order (SortRows :477-508: the keys are ranked, ties by index as in
+// tiers 2-4) and output.  Rows that belong to the padding are exact unit vectors on a padding
+// column and are left out.  One block per matrix.
+template <typename T, bool EVECS>
+__global__ void __launch_bounds__(256)
+blk_finalize_kernel(const T* __restrict__ Mw, const T* __restrict__ Ew, const int* __restrict__ rot_total,
+                    const int* __restrict__ converged, T* __restrict__ evals, T* __restrict__ evecs,
+                    int* __restrict__ n_iters, int n, int np, long long batch, long long b0, int soa,
+                    int sort_criteria, int max_num_sweeps) {
+  extern __shared__ __align__(16) unsigned char bj_smem_raw[];
+  T* key = reinterpret_cast<T*>(bj_smem_raw);            // [np] diagonal of M
+  int* is_pad = reinterpret_cast<int*>(key + np);        // [np] row belongs to the padding
+  int* pos_of = is_pad + np;                             // [np] output position of row r
+  const int lb = blockIdx.x;
+  const long long b = b0 + lb;
+  const T* M = Mw + (size_t)lb * np * np;
+  const T* E = Ew + (size_t)lb * np * np;
+  for (int r = threadIdx.x; r < np; r += blockDim.x) {
+    bool pad = false;
+    for (int c = n; c < np; ++c) pad = pad || !is_zero(E[(size_t)r * np + c]);
+    key[r] = M[(size_t)r * np + r];
+    is_pad[r] = pad ? 1 : 0;
+  }
+  __syncthreads();
+  const bool sorted = sort_criteria >= SORT_DECREASING_EVALS && sort_criteria <= SORT_INCREASING_ABS_EVALS;
+  const bool use_abs = sort_criteria >= SORT_DECREASING_ABS_EVALS;
+  const bool decreasing = (sort_criteria == SORT_DECREASING_EVALS) || (sort_criteria == SORT_DECREASING_ABS_EVALS);
+  for (int r = threadIdx.x; r < np; r += blockDim.x) {
+    int rank = np;                                        // padding rows: beyond every output row
+    if (!is_pad[r]) {
+      const T mine = use_abs ? jabs(key[r]) : key[r];
+      rank = 0;
+      for (int j = 0; j < np; ++j) {
+        if (j == r || is_pad[j]) continue;
+        const T other = use_abs ? jabs(key[j]) : key[j];
+        const bool strictly = sorted && (decreasing ? (other > mine) : (other < mine));
+        const bool tie = !sorted || other == mine;
+        rank += (strictly || (tie && j < r)) ? 1 : 0;
+      }
+    }
+    pos_of[r] = rank;
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < np; r += blockDim.x) {
+    const int pos = pos_of[r];
+    if (pos < n) {
+      if (soa) evals[(size_t)pos * (size_t)batch + (size_t)b] = key[r];
+      else evals[(size_t)b * n + pos] = key[r];
+    }
+  }
+  if (threadIdx.x == 0 && n_iters) n_iters[b] = (converged[lb] && max_num_sweeps > 0) ? rot_total[lb] + 1 : 0;
+  if (EVECS) {
+    for (int r = 0; r < np; ++r) {
+      const int pos = pos_of[r];
+      if (pos >= n) continue;
+      for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        const T v = E[(size_t)r * np + c];
+        const size_t e_idx = (size_t)pos * n + c;
+        if (soa) evecs[e_idx * (size_t)batch + (size_t)b] = v;
+        else evecs[(size_t)b * n * n + e_idx] = v;
+      }
+    }
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace jpd

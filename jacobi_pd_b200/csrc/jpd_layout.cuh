@@ -7,8 +7,13 @@
 //   2 packed AoS       m[b*T + t(i,j)], j >= i      (upper triangle only, T = n(n+1)/2)
 //   3 packed SoA       m[t(i,j)*batch + b], j >= i
 //   4 pointer array    ptrs[b][i*n + j]             (scattered matrices, source only)
-// reading and writing 32 consecutive scalars per warp on both sides (32 x 33 shared tile),
-// i.e. at HBM speed.  Packed sources are mirrored into the lower triangle of full targets.
+// reading and writing 32 consecutive scalars per warp on both sides (32 x 33 shared tile).
+// Packed sources are mirrored into the lower triangle of full targets.
+// The callers' own sizes (n <= 16: nine or sixteen scalars per matrix) would leave most lanes of
+// a 32-wide tile row idle on the AoS side, so AoS <-> SoA of small matrices goes through
+// jpd_convert_flat_kernel instead: the AoS side is treated as ONE flat array (a warp always
+// touches 32 consecutive scalars, across matrix boundaries), the SoA side as planes.
+// Measured GB/s against the HBM copy peak: bench.py "layout_adapter".
 #pragma once
 #include "jpd_common.cuh"
 
@@ -69,6 +74,50 @@ jpd_convert_kernel(const void* __restrict__ src, int src_layout, T* __restrict__
         const T v = bf ? tile[tx][r] : tile[r][tx];
         if (bf) dst[s * batch + b] = v; else dst[b * dst_per + s] = v;
       }
+    }
+  }
+}
+
+// AoS <-> SoA for small matrices (nn = n*n <= 256).  One block moves `tb` consecutive matrices
+// (tb a power of two >= 32) through a shared tile with an odd row pitch (conflict-free on the
+// plane side, where the 32 lanes of a warp read 32 different matrices).
+template <typename T, bool TO_SOA>
+__global__ void __launch_bounds__(256)
+jpd_convert_flat_kernel(const T* __restrict__ src, T* __restrict__ dst, int nn, long long batch, int tb, int tb_shift) {
+  extern __shared__ __align__(16) unsigned char jpd_flat_raw[];
+  T* tile = reinterpret_cast<T*>(jpd_flat_raw);
+  const int pitch = nn | 1;
+  const long long b0 = (long long)blockIdx.x * tb;
+  const long long left = batch - b0;
+  const int nb = left < tb ? (int)left : tb;
+  const int total = nb * nn;
+  const int tid = threadIdx.x;
+  const T* aos_in = src + b0 * nn;
+  T* aos_out = dst + b0 * nn;
+  // flat AoS index f = bl * nn + e, advanced by 256 per iteration without a division
+  int e = tid % nn, bl = tid / nn;
+  const int de = 256 % nn, db = 256 / nn;
+  if (TO_SOA) {
+    for (int f = tid; f < total; f += 256) {
+      tile[bl * pitch + e] = aos_in[f];
+      e += de; bl += db;
+      if (e >= nn) { e -= nn; ++bl; }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < (nn << tb_shift); idx += 256) {
+      const int pe = idx >> tb_shift, pb = idx & (tb - 1);
+      if (pb < nb) dst[(long long)pe * batch + b0 + pb] = tile[pb * pitch + pe];
+    }
+  } else {
+    for (int idx = tid; idx < (nn << tb_shift); idx += 256) {
+      const int pe = idx >> tb_shift, pb = idx & (tb - 1);
+      if (pb < nb) tile[pb * pitch + pe] = src[(long long)pe * batch + b0 + pb];
+    }
+    __syncthreads();
+    for (int f = tid; f < total; f += 256) {
+      aos_out[f] = tile[bl * pitch + e];
+      e += de; bl += db;
+      if (e >= nn) { e -= nn; ++bl; }
     }
   }
 }

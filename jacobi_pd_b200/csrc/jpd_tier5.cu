@@ -3,30 +3,42 @@
 #include <mutex>
 
 #include "jpd_internal.h"
-#include "jpd_block.cuh"
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "jpd_blockjacobi.cuh"
 #include "jpd_layout.cuh"
 
 namespace jpd_host {
 using namespace jpd;
 
 namespace {
-// ------------------------------------------------------------------ tier 5 plan + launch
-BlockPlan make_block_plan(int n, int elem, int calc, int smem_limit) {
-  BlockPlan p{};
-  const int m = n + (n & 1), half = m / 2;
-  p.ldm = n | 1;
-  const size_t base = (size_t)(2 * half + n) * elem + (size_t)(n + 4) * sizeof(int) + 16;
-  const size_t mb = (size_t)n * p.ldm * elem;
-  const size_t eb = calc ? (size_t)n * n * elem : 0;
-  if (base + mb + eb <= (size_t)smem_limit) { p.m_in_smem = 1; p.e_in_smem = 1; }
-  else if (base + mb <= (size_t)smem_limit) { p.m_in_smem = 1; p.e_in_smem = 0; }
-  else { p.m_in_smem = 0; p.e_in_smem = 0; }
-  p.smem_bytes = base + (p.m_in_smem ? mb : 0) + (p.e_in_smem ? eb : 0);
-  p.work_elems = (p.m_in_smem ? 0 : (size_t)n * p.ldm) + ((p.e_in_smem || !calc) ? 0 : (size_t)n * n);
-  const long long items = (long long)half * (half - 1) / 2 + (calc ? (long long)half * n : 0);
-  long long thr = ((items / 4) + 31) / 32 * 32;
-  p.threads = (int)std::min<long long>(1024, std::max<long long>(32, thr));
-  return p;
+// ------------------------------------------------------------------ tier 5: block Jacobi (jpd_blockjacobi.cuh)
+// round-robin tournament of nb (even) block indices: step s in [0, nb-1) -> nb/2 disjoint pairs
+void block_pairs(int nb, int step, std::vector<int2>& out) {
+  out.clear();
+  const int m = nb - 1;
+  for (int k = 0; k < nb / 2; ++k) {
+    int a = (k == 0) ? m : (step + k) % m;
+    int b = (k == 0) ? step : (step - k + m) % m;
+    if (a > b) std::swap(a, b);
+    out.push_back(make_int2(a, b));
+  }
+}
+
+// inner sweeps of a pivot solve: full convergence of every 64 x 64 block is not needed for the
+// outer iteration to converge (quadratically); JPD_BLOCK_INNER_SWEEPS overrides (tuning aid)
+int inner_sweeps() {
+  static int v = -1;
+  if (v < 0) {
+    v = 50;
+    if (const char* env = std::getenv("JPD_BLOCK_INNER_SWEEPS")) {
+      const long x = std::strtol(env, nullptr, 10);
+      if (x >= 1 && x <= 50) v = (int)x;
+    }
+  }
+  return v;
 }
 
 template <typename T>
@@ -34,32 +46,101 @@ int launch_block(const T* mat, T* evals, T* evecs, int* iters, int n, long long 
                  int sort, int calc, int sweeps, cudaStream_t st) {
   int dev = 0;
   JPD_CK(cudaGetDevice(&dev));
-  DeviceInfo info;
-  int rc = device_info(dev, &info);
-  if (rc != JPD_OK) return rc;
-  const BlockPlan plan = make_block_plan(n, (int)sizeof(T), calc, info.smem_optin);
-  auto kernel = jpd_block_kernel<T>;
-  if (plan.smem_bytes > 48 * 1024)
-    JPD_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
-  int per_sm = 1;
-  JPD_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, plan.threads, plan.smem_bytes));
-  if (per_sm < 1) return JPD_ERR_UNSUPPORTED;
-  const long long resident = (long long)per_sm * info.sm_count;
-  const long long grid = std::min<long long>(batch, resident);
+  keep_freed_workspace_cached(dev);
+  const int np = (n + kBjPivot - 1) / kBjPivot * kBjPivot;
+  const int nb = np / kBjBlock, npairs = nb / 2, nsteps = nb - 1;
+  const size_t mat_elems = (size_t)np * np;
+  const int soa = layout == JPD_LAYOUT_SOA ? 1 : 0;
 
-  T* work = nullptr;
-  if (plan.work_elems) {
-    keep_freed_workspace_cached(dev);
-    JPD_CK(cudaMallocAsync((void**)&work, plan.work_elems * sizeof(T) * (size_t)grid, st));
+  // matrices per pass: workspace (M, E, pivots, Q) capped at ~6 GB
+  const size_t per_matrix = sizeof(T) * (2 * mat_elems + (size_t)npairs * (2 * 4096 + 64)) + 64;
+  long long group = std::max<long long>(1, (long long)(((size_t)6 << 30) / per_matrix));
+  group = std::min(group, batch);
+
+  T *Mw = nullptr, *Ew = nullptr, *P = nullptr, *Q = nullptr, *pev = nullptr;
+  int *piv_it = nullptr, *counters = nullptr;
+  int2* d_pairs = nullptr;
+  int2* h_pairs = nullptr;
+  int* h_flag = nullptr;
+  int status = JPD_OK;
+  cudaError_t err = cudaSuccess;
+  const char* what = "";
+#define BJ_TRY(expr) do { if (err == cudaSuccess) { err = (expr); if (err != cudaSuccess) what = #expr; } } while (0)
+  BJ_TRY(cudaMallocAsync((void**)&Mw, sizeof(T) * mat_elems * group, st));
+  BJ_TRY(cudaMallocAsync((void**)&Ew, sizeof(T) * mat_elems * group, st));
+  BJ_TRY(cudaMallocAsync((void**)&P, sizeof(T) * 4096 * npairs * group, st));
+  BJ_TRY(cudaMallocAsync((void**)&Q, sizeof(T) * 4096 * npairs * group, st));
+  BJ_TRY(cudaMallocAsync((void**)&pev, sizeof(T) * 64 * npairs * group, st));
+  BJ_TRY(cudaMallocAsync((void**)&piv_it, sizeof(int) * npairs * group, st));
+  BJ_TRY(cudaMallocAsync((void**)&counters, sizeof(int) * (3 * group + 1), st));   // rot_total | rot_sweep | converged | any_left
+  BJ_TRY(cudaMallocAsync((void**)&d_pairs, sizeof(int2) * npairs * nsteps, st));
+  BJ_TRY(cudaMallocHost((void**)&h_pairs, sizeof(int2) * npairs * nsteps));
+  BJ_TRY(cudaMallocHost((void**)&h_flag, sizeof(int)));
+  if (err == cudaSuccess) {
+    std::vector<int2> pr;
+    for (int s = 0; s < nsteps; ++s) {
+      block_pairs(nb, s, pr);
+      std::memcpy(h_pairs + (size_t)s * npairs, pr.data(), sizeof(int2) * npairs);
+    }
+    BJ_TRY(cudaMemcpyAsync(d_pairs, h_pairs, sizeof(int2) * npairs * nsteps, cudaMemcpyHostToDevice, st));
   }
-  kernel<<<dim3((unsigned)grid), dim3(plan.threads), plan.smem_bytes, st>>>(
-      mat, evals, evecs, iters, n, batch, layout == JPD_LAYOUT_SOA ? 1 : 0, sort, calc, sweeps,
-      plan.ldm, plan.m_in_smem, plan.e_in_smem, work, plan.work_elems);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  cudaError_t le = cudaGetLastError();
-  if (work) cudaFreeAsync(work, st);
-  JPD_CK(le);
-  return JPD_OK;
+  const size_t apply_smem = sizeof(T) * 3 * kBjPivot * kBjLd;
+  auto apply = calc ? blk_apply_kernel<T, true> : blk_apply_kernel<T, true>;   // E is always kept: it marks the padding rows
+  BJ_TRY(cudaFuncSetAttribute(apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem));
+  const int ntile = npairs * (npairs + 1) / 2;
+  const int items = ntile + npairs * (np / kBjPivot);
+
+  for (long long b0 = 0; b0 < batch && err == cudaSuccess && status == JPD_OK; b0 += group) {
+    const long long cnt = std::min(group, batch - b0);
+    int* rot_total = counters; int* rot_sweep = counters + group; int* converged = counters + 2 * group;
+    int* any_left = counters + 3 * group;
+    BJ_TRY(cudaMemsetAsync(counters, 0, sizeof(int) * (3 * group + 1), st));
+    const long long init_blocks = std::min<long long>((cnt * (long long)mat_elems + 255) / 256, 148 * 64);
+    blk_init_kernel<T><<<(unsigned)init_blocks, 256, 0, st>>>(mat, Mw, Ew, n, np, batch, b0, cnt, soa);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    const unsigned cb = (unsigned)((cnt + 127) / 128);
+    for (int sweep = 0; sweep < sweeps && err == cudaSuccess && status == JPD_OK; ++sweep) {
+      BJ_TRY(cudaMemsetAsync(any_left, 0, sizeof(int), st));
+      for (int s = 0; s < nsteps && status == JPD_OK; ++s) {
+        const int2* prs = d_pairs + (size_t)s * npairs;
+        blk_gather_kernel<T><<<dim3(npairs, (unsigned)cnt), kBjThreads, 0, st>>>(Mw, P, prs, npairs, np);
+        status = launch_tier3<T>(P, pev, Q, piv_it, kBjPivot, (long long)npairs * cnt, JPD_LAYOUT_AOS, 0 /* DO_NOT_SORT */,
+                                 1, inner_sweeps(), st);
+        if (status != JPD_OK) break;
+        apply<<<dim3(items, (unsigned)cnt), kBjThreads, apply_smem, st>>>(Mw, Ew, Q, prs, npairs, np);
+        blk_count_kernel<<<cb, 128, 0, st>>>(piv_it, npairs, cnt, rot_total, rot_sweep, any_left);
+        g_launches.fetch_add(3, std::memory_order_relaxed);
+      }
+      blk_sweep_end_kernel<<<cb, 128, 0, st>>>(rot_sweep, converged, cnt);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      BJ_TRY(cudaGetLastError());
+      BJ_TRY(cudaMemcpyAsync(h_flag, any_left, sizeof(int), cudaMemcpyDeviceToHost, st));
+      BJ_TRY(cudaStreamSynchronize(st));     // one flag per outer sweep
+      if (err == cudaSuccess && *h_flag == 0) break;   // a whole sweep without a rotation, for every matrix
+    }
+    if (err != cudaSuccess || status != JPD_OK) break;
+    const size_t fin_smem = sizeof(T) * np + sizeof(int) * 2 * np;
+    if (calc) blk_finalize_kernel<T, true><<<(unsigned)cnt, 256, fin_smem, st>>>(Mw, Ew, rot_total, converged, evals, evecs, iters,
+                                                                                n, np, batch, b0, soa, sort, sweeps);
+    else      blk_finalize_kernel<T, false><<<(unsigned)cnt, 256, fin_smem, st>>>(Mw, Ew, rot_total, converged, evals, evecs, iters,
+                                                                                 n, np, batch, b0, soa, sort, sweeps);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    BJ_TRY(cudaGetLastError());
+  }
+#undef BJ_TRY
+  if (h_pairs || h_flag) cudaStreamSynchronize(st);   // the pinned scratch must outlive the copies that use it
+  if (Mw) cudaFreeAsync(Mw, st);
+  if (Ew) cudaFreeAsync(Ew, st);
+  if (P) cudaFreeAsync(P, st);
+  if (Q) cudaFreeAsync(Q, st);
+  if (pev) cudaFreeAsync(pev, st);
+  if (piv_it) cudaFreeAsync(piv_it, st);
+  if (counters) cudaFreeAsync(counters, st);
+  if (d_pairs) cudaFreeAsync(d_pairs, st);
+  if (h_pairs) cudaFreeHost(h_pairs);
+  if (h_flag) cudaFreeHost(h_flag);
+  if (err != cudaSuccess) { set_last_cuda_error(what, err); return JPD_ERR_CUDA; }
+  return status;
 }
 
 }  // namespace
@@ -78,6 +159,23 @@ int convert_layout(const void* src, int src_layout, T* dst, int dst_layout, int 
   if (dst_layout < kLayoutAoS || dst_layout > kLayoutPackedSoA) return JPD_ERR_INVALID_ARG;
   if (batch == 0) return JPD_OK;
   if (!src || !dst) return JPD_ERR_INVALID_ARG;
+  const int nn = n * n;
+  if (nn <= 256 && ((src_layout == kLayoutAoS && dst_layout == kLayoutSoA) || (src_layout == kLayoutSoA && dst_layout == kLayoutAoS))) {
+    const int tb_shift = nn <= 32 ? 7 : (nn <= 64 ? 6 : 5), tb = 1 << tb_shift;
+    const long long blocks = (batch + tb - 1) / tb;
+    if (blocks > 0x7fffffffLL) return JPD_ERR_UNSUPPORTED;
+    const size_t smem = sizeof(T) * (size_t)tb * (nn | 1);
+    if (src_layout == kLayoutAoS) {
+      if (smem > 48 * 1024) JPD_CK(cudaFuncSetAttribute(jpd_convert_flat_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      jpd_convert_flat_kernel<T, true><<<(unsigned)blocks, 256, smem, st>>>(static_cast<const T*>(src), dst, nn, batch, tb, tb_shift);
+    } else {
+      if (smem > 48 * 1024) JPD_CK(cudaFuncSetAttribute(jpd_convert_flat_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      jpd_convert_flat_kernel<T, false><<<(unsigned)blocks, 256, smem, st>>>(static_cast<const T*>(src), dst, nn, batch, tb, tb_shift);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    JPD_CK(cudaGetLastError());
+    return JPD_OK;
+  }
   const long long bx = (batch + 31) / 32;
   const long long by = ((long long)n * n + 31) / 32;
   if (bx > 0x7fffffffLL || by > 65535) return JPD_ERR_UNSUPPORTED;

@@ -70,13 +70,47 @@ def test_parity_large(n, dtype):
         assert np.array_equal(x, y)
 
 
+def _random_symmetric(n, batch, dtype, seed):
+    rng = np.random.default_rng(seed)            # (the counter generator stops at n = 256)
+    A = rng.uniform(-1, 1, (batch, n, n))
+    return np.ascontiguousarray((np.triu(A) + np.triu(A, 1).swapaxes(1, 2)).astype(dtype))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("n", [257, 300])
-def test_parity_beyond_cluster_tier(n):
-    rng = np.random.default_rng(9000 + n)        # (the counter generator stops at n = 256)
-    A = rng.uniform(-1, 1, (2, n, n))
-    A = np.ascontiguousarray(np.triu(A) + np.triu(A, 1).swapaxes(1, 2))
-    ref = ob.oracle_diagonalize(A, 1)
-    parity.full_check(A, run_gpu(A, 1), ref, 1)
+def test_parity_block_jacobi_tier_vs_oracle(n, dtype):
+    """tier 5 (block Jacobi over the whole device, jpd_blockjacobi.cuh) at sizes the oracle still
+    finishes in seconds: all sort criteria, both layouts, calc_evecs off, max_num_sweeps = 0"""
+    A = _random_symmetric(n, 3, dtype, 9000 + n)
+    for sort in (1, 2, 3, 4, 0):
+        ref = ob.oracle_diagonalize(A, sort)
+        out = run_gpu(A, sort, layout=sort & 1)
+        parity.full_check(A, out, ref, sort)
+    ev, vec, it = run_gpu(A, 1, calc=False)
+    assert vec is None
+    parity.check_evals(ev, ob.oracle_diagonalize(A, 1)[0])
+    ref0 = ob.oracle_diagonalize(A, 1, True, 0)
+    ev0, vec0, it0 = run_gpu(A, 1, sweeps=0)
+    assert (it0 == 0).all() and np.array_equal(ev0, ref0[0]) and np.array_equal(vec0, ref0[1])
+    a, b = run_gpu(A, 1), run_gpu(A[:1], 1)      # a matrix's result does not depend on its batch
+    assert np.array_equal(a[0][:1], b[0]) and np.array_equal(a[1][:1], b[1])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("n", [384, 512, 1000])
+def test_block_jacobi_tier_large(n, layout, dtype):
+    """The sizes the reference benchmarks beyond the configs (benchmarks/README.md:19-20).  The
+    oracle needs minutes per matrix here, so eigenvalues are checked against LAPACK
+    (numpy.linalg.eigvalsh, fp64) with the north-star tolerance, eigenvectors through the
+    size-independent properties: residual, orthonormality, order."""
+    A = _random_symmetric(n, 2, dtype, 7000 + n)
+    ev, vec, it = run_gpu(A, 1, layout=layout)
+    assert (it > 0).all()
+    lap = np.linalg.eigvalsh(A.astype(np.float64))[:, ::-1]
+    parity.check_evals(ev, lap.astype(dtype))
+    parity.check_sorted(ev, 1)
+    parity.check_residual_orth(A, ev, vec)
 
 
 def test_host_api_matches_device_api():
