@@ -64,6 +64,18 @@ template <> struct Abi<double> {
                   void *stream) {
     return jpd_principal_axes_f64(i6, mom, ax, it, b, layout, sweeps, stream);
   }
+  static int host_packed(const double *m, double *ev, double *vec, int *it, int n, long long b, int layout, int sort,
+                         int calc, int sweeps, int device_id) {
+    return jpd_diagonalize_batched_host_packed_f64(m, ev, vec, it, n, b, layout, sort, calc, sweeps, device_id);
+  }
+  static int quaternion_host(const double *c, double *lam, double *q, int *it, long long b, int layout, int all,
+                             int sweeps, int device_id) {
+    return jpd_quaternion_from_correlation_host_f64(c, lam, q, it, b, layout, all, sweeps, device_id);
+  }
+  static int axes_host(const double *i6, double *mom, double *ax, int *it, long long b, int layout, int sweeps,
+                       int device_id) {
+    return jpd_principal_axes_host_f64(i6, mom, ax, it, b, layout, sweeps, device_id);
+  }
 };
 template <> struct Abi<float> {
   static int device(const float *m, float *ev, float *vec, int *it, int n, long long b, int layout, int sort,
@@ -86,6 +98,18 @@ template <> struct Abi<float> {
                   void *stream) {
     return jpd_principal_axes_f32(i6, mom, ax, it, b, layout, sweeps, stream);
   }
+  static int host_packed(const float *m, float *ev, float *vec, int *it, int n, long long b, int layout, int sort,
+                         int calc, int sweeps, int device_id) {
+    return jpd_diagonalize_batched_host_packed_f32(m, ev, vec, it, n, b, layout, sort, calc, sweeps, device_id);
+  }
+  static int quaternion_host(const float *c, float *lam, float *q, int *it, long long b, int layout, int all,
+                             int sweeps, int device_id) {
+    return jpd_quaternion_from_correlation_host_f32(c, lam, q, it, b, layout, all, sweeps, device_id);
+  }
+  static int axes_host(const float *i6, float *mom, float *ax, int *it, long long b, int layout, int sweeps,
+                       int device_id) {
+    return jpd_principal_axes_host_f32(i6, mom, ax, it, b, layout, sweeps, device_id);
+  }
 };
 
 }  // namespace detail
@@ -98,6 +122,9 @@ enum class Layout : int { AoS = JPD_LAYOUT_AOS, SoAInterleaved = JPD_LAYOUT_SOA 
 // ---------------------------------------------------------------------------------------
 template <typename Scalar, typename Vector, typename Matrix, typename ConstMatrix = Matrix>
 class Jacobi {
+  // The reference is generic in Scalar (jacobi_pd.hpp:25); the device computes in fp64 or fp32
+  // only.  Any other Scalar (long double, a multiprecision type, ...) would have to be rounded
+  // to double behind the caller's back, so it is refused at compile time.
   static_assert(std::is_same<Scalar, double>::value || std::is_same<Scalar, float>::value,
                 "the GPU path computes in fp64 or fp32");
   int n;                         // matrix size (rows)
@@ -229,6 +256,44 @@ struct BatchedJacobi {
                                                  static_cast<int>(layout), all_eigenpairs ? 1 : 0,
                                                  max_num_sweeps, cuda_stream),
                   "jacobi_pd::BatchedJacobi::QuaternionFromCorrelation");
+  }
+
+  /// Host-resident batch given as packed upper triangles (n(n+1)/2 scalars per matrix -- all the
+  /// reference reads, jacobi_pd.hpp:167-171): less PCIe traffic than DiagonalizeHost.
+  static void DiagonalizeHostPacked(const Scalar *h_upper, Scalar *h_evals, Scalar *h_evecs, int *h_n_iters, int n,
+                                    long long batch, Layout layout = Layout::AoS,
+                                    int sort_criteria = JPD_SORT_DECREASING_EVALS, bool calc_evecs = true,
+                                    int max_num_sweeps = 50, int device = 0) {
+    detail::check(detail::Abi<Scalar>::host_packed(h_upper, h_evals, h_evecs, h_n_iters, n, batch,
+                                                  static_cast<int>(layout), sort_criteria, calc_evecs ? 1 : 0,
+                                                  max_num_sweeps, device),
+                  "jacobi_pd::BatchedJacobi::DiagonalizeHostPacked");
+  }
+
+  /// QuaternionFromCorrelation / PrincipalAxes with HOST buffers, streamed through one GPU like
+  /// DiagonalizeHost (colvars: 72 B up + 44 B down per frame instead of 128 + 168 B).
+  static void QuaternionFromCorrelationHost(const Scalar *h_corr, Scalar *h_lambda, Scalar *h_quat, int *h_n_iters,
+                                            long long batch, Layout layout = Layout::AoS,
+                                            bool all_eigenpairs = false, int max_num_sweeps = 50, int device = 0) {
+    detail::check(detail::Abi<Scalar>::quaternion_host(h_corr, h_lambda, h_quat, h_n_iters, batch,
+                                                      static_cast<int>(layout), all_eigenpairs ? 1 : 0,
+                                                      max_num_sweeps, device),
+                  "jacobi_pd::BatchedJacobi::QuaternionFromCorrelationHost");
+  }
+  static void PrincipalAxesHost(const Scalar *h_inertia6, Scalar *h_moments, Scalar *h_axes, int *h_n_iters,
+                                long long batch, Layout layout = Layout::AoS, int max_num_sweeps = 50,
+                                int device = 0) {
+    detail::check(detail::Abi<Scalar>::axes_host(h_inertia6, h_moments, h_axes, h_n_iters, batch,
+                                                static_cast<int>(layout), max_num_sweeps, device),
+                  "jacobi_pd::BatchedJacobi::PrincipalAxesHost");
+  }
+
+  /// Page-lock / release a caller-owned host buffer so that the host entries overlap copies and kernels.
+  static void HostRegister(void *h_ptr, std::size_t bytes) {
+    detail::check(jpd_host_register(h_ptr, static_cast<unsigned long long>(bytes)), "jacobi_pd::BatchedJacobi::HostRegister");
+  }
+  static void HostUnregister(void *h_ptr) {
+    detail::check(jpd_host_unregister(h_ptr), "jacobi_pd::BatchedJacobi::HostUnregister");
   }
 
   /// LAMMPS rigid bodies, fused: (Ixx, Iyy, Izz, Iyz, Ixz, Ixy) per body -> principal moments

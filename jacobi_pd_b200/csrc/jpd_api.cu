@@ -66,6 +66,20 @@ namespace {
 
 using namespace jpd_host;
 
+// smallest n that goes to the block-Jacobi tier (default: everything beyond the cluster tier);
+// JPD_BLOCK_MIN_N (> 128) moves the boundary down -- tuning aid for the tier-4 / tier-5 crossover
+int block_tier_min_n() {
+  static int v = -1;
+  if (v < 0) {
+    v = kClusterMaxN + 1;
+    if (const char* env = std::getenv("JPD_BLOCK_MIN_N")) {
+      const long x = std::strtol(env, nullptr, 10);
+      if (x > kCtaMaxN && x <= kClusterMaxN + 1) v = (int)x;
+    }
+  }
+  return v;
+}
+
 // ------------------------------------------------------------------ device entry
 template <typename T>
 int diagonalize_device(const T* mat, T* evals, T* evecs, int* iters, int n, long long batch,
@@ -79,7 +93,8 @@ int diagonalize_device(const T* mat, T* evals, T* evecs, int* iters, int n, long
   if (n <= kSmallMaxN) return launch_tier1<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
   if (n <= kWarpMaxN) return launch_tier2<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
   if (n <= kCtaMaxN) return launch_tier3<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
-  if (n <= kClusterMaxN) return launch_tier4<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
+  if (n <= kClusterMaxN && n < block_tier_min_n())
+    return launch_tier4<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
   return launch_tier5<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
 }
 

@@ -1,7 +1,9 @@
 // Exercises the C++ front end (include/jacobi_pd_cuda.hpp) end to end on the GPU:
 //  - jacobi_pd::Jacobi on the README example of the reference (README.md:58-99)
 //  - jacobi_pd::BatchedJacobi<double>::DiagonalizeHost on a small AoS batch, checked by
-//    residual / orthogonality / ordering.  Exit code 0 = pass.  Run by tests/test_gpu_dropin.py.
+//    residual / orthogonality / ordering;
+//  - DiagonalizeHostPacked, QuaternionFromCorrelationHost, HostRegister against the plain entry.
+// Exit code 0 = pass.  Run by tests/test_gpu_dropin.py.
 #include <cmath>
 #include <cstdio>
 #include <vector>
@@ -69,6 +71,41 @@ int main() {
           if (std::fabs(d) > 4e-12) return fail("batched: orthogonality");
         }
       }
+    }
+  }
+  {  // packed upper-triangle host input and the fused colvars host entry: same results as the plain ones
+    const int n = 4;
+    const long long B = 500;
+    std::vector<double> corr(B * 9), mat(B * 16), packed(B * 10), ev(B * 4), vec(B * 16), ev2(B * 4), vec2(B * 16);
+    std::vector<double> lam(B), quat(B * 4);
+    std::vector<int> iters(B);
+    unsigned long long s = 1234567ull;
+    for (long long b = 0; b < B; ++b) {
+      double R[9];
+      for (int e = 0; e < 9; ++e) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        R[e] = corr[b * 9 + e] = (double)(s >> 11) / 9007199254740992.0 * 2.0 - 1.0;
+      }
+      const double xx = R[0], xy = R[1], xz = R[2], yx = R[3], yy = R[4], yz = R[5], zx = R[6], zy = R[7], zz = R[8];
+      const double S[4][4] = {{(xx + yy) + zz, yz - zy, zx - xz, xy - yx},
+                              {0, (xx - yy) - zz, xy + yx, zx + xz},
+                              {0, 0, (yy - xx) - zz, yz + zy},
+                              {0, 0, 0, (zz - xx) - yy}};
+      int t = 0;
+      for (int i = 0; i < n; ++i)
+        for (int j = i; j < n; ++j) { mat[b * 16 + i * n + j] = mat[b * 16 + j * n + i] = S[i][j]; packed[b * 10 + t++] = S[i][j]; }
+    }
+    BatchedJacobi<double>::HostRegister(mat.data(), mat.size() * sizeof(double));
+    BatchedJacobi<double>::DiagonalizeHost(mat.data(), ev.data(), vec.data(), iters.data(), n, B);
+    BatchedJacobi<double>::HostUnregister(mat.data());
+    BatchedJacobi<double>::DiagonalizeHostPacked(packed.data(), ev2.data(), vec2.data(), iters.data(), n, B);
+    if (ev != ev2 || vec != vec2) return fail("packed host input differs from the full input");
+    BatchedJacobi<double>::QuaternionFromCorrelationHost(corr.data(), lam.data(), quat.data(), iters.data(), B);
+    for (long long b = 0; b < B; ++b) {
+      if (lam[b] != ev[b * 4]) return fail("fused host entry: leading eigenvalue differs");
+      if (quat[b * 4] < 0) return fail("fused host entry: q0 < 0");
+      for (int v = 0; v < 4; ++v)
+        if (std::fabs(std::fabs(quat[b * 4 + v]) - std::fabs(vec[b * 16 + v])) != 0) return fail("fused host entry: quaternion differs");
     }
   }
   std::printf("test passed\n");

@@ -108,7 +108,10 @@ def test_block_jacobi_tier_large(n, layout, dtype):
     ev, vec, it = run_gpu(A, 1, layout=layout)
     assert (it > 0).all()
     lap = np.linalg.eigvalsh(A.astype(np.float64))[:, ::-1]
-    parity.check_evals(ev, lap.astype(dtype))
+    # north-star tolerance (1e-12 fp64 / 1e-5 fp32, stated for the configs' n <= 256), but never
+    # below what rounding alone allows at this size: n * eps / 2 (fp32, n = 1000: 3e-5)
+    tol = max(parity.TOL[np.dtype(dtype)], 0.5 * n * np.finfo(dtype).eps)
+    parity.check_evals(ev, lap.astype(dtype), tol=tol)
     parity.check_sorted(ev, 1)
     parity.check_residual_orth(A, ev, vec)
 
