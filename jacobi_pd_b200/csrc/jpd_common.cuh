@@ -229,8 +229,9 @@ JPD_HD bool pair_needs_rotation(T a, T mii, T mjj) {
 // from sin2θ / 2c, never from 1 - c^2).  d and a are pre-scaled by a power of two
 // when x could overflow or underflow (warp-uniform rare path): c, s, t are
 // scale-invariant, so huge / tiny / denormal inputs keep full accuracy.
+// (u = 1/c is returned as well: the scaled-rotation tiers track reciprocal row scales with it)
 template <typename T>
-JPD_HD void rotation_from_scaled(T d, T a, bool d_is_zero, bool d_neg, T& c, T& s, T& t) {
+JPD_HD void rotation_from_scaled(T d, T a, bool d_is_zero, bool d_neg, T& c, T& s, T& t, T& u) {
   const T a2 = a + a;
   const T x = jfma(a2, a2, d * d);
   const T p = rsqrt_refined(x);
@@ -241,10 +242,15 @@ JPD_HD void rotation_from_scaled(T d, T a, bool d_is_zero, bool d_neg, T& c, T& 
   const bool flip = d_is_zero ? sign_bit(a) : d_neg;
   sp = flip ? -sp : sp;
   const T v = jfma(T(0.5), rho, T(0.5));
-  const T u = rsqrt_refined(v);
+  u = rsqrt_refined(v);
   c = v * u;
   s = (T(0.5) * sp) * u;
   t = s * u;
+}
+template <typename T>
+JPD_HD void rotation_from_scaled(T d, T a, bool d_is_zero, bool d_neg, T& c, T& s, T& t) {
+  T u;
+  rotation_from_scaled(d, a, d_is_zero, d_neg, c, s, t, u);
 }
 
 template <typename T>

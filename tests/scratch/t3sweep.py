@@ -1,0 +1,14 @@
+# dev tool: tier-3 size sweep, both kernels (JPD_TIER3_LEGACY toggled per process)
+import sys, os; sys.path.insert(0, '.')
+import torch, jacobi_pd_b200 as jpd
+for dt in (torch.float64, torch.float32):
+    for n in (33, 40, 48, 56, 64, 72, 80, 96, 112, 128):
+        B = 4096 if n <= 64 else 1184
+        m = torch.empty((B, n, n), dtype=dt, device='cuda'); jpd.fill_synthetic(m, n, B, 0, 0, 1234)
+        out = jpd.diagonalize_batched(m, layout=0); torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(2):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); jpd.diagonalize_batched(m, layout=0, out=out); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        print(f"legacy={os.environ.get('JPD_TIER3_LEGACY','0')} {str(dt)[6:]} n={n} {best:.2f} ms {B/best*1e3:.4e}", flush=True)
