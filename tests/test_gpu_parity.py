@@ -70,6 +70,28 @@ def test_parity_large(n, dtype):
         assert np.array_equal(x, y)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [33, 41, 52, 53, 57, 63, 65, 81, 97, 98, 99, 111, 127])
+def test_parity_tier3_both_kernels(n, dtype):
+    """tier 3 dispatches between the first-generation kernel (2x2 blocks) and the block-ordering kernel
+    (4x4 register tiles, scaled eigenvector rotations) by size and precision: sizes on both sides of
+    every switch point, every padding (n mod 4), all sort criteria on one of them"""
+    A = ob.fill_synthetic(n, 12, seed=4000 + n, dtype=dtype)
+    ref = ob.oracle_diagonalize(A, 1)
+    for layout in (0, 1):
+        out = run_gpu(A, 1, layout=layout)
+        parity.full_check(A, out, ref, 1)
+    if n in (57, 99):
+        for sort in (0, 2, 3, 4):
+            parity.full_check(A, run_gpu(A, sort), ob.oracle_diagonalize(A, sort), sort)
+        ev, vec, it = run_gpu(A, 1, calc=False)
+        assert vec is None
+        parity.check_evals(ev, ref[0])
+        ref0 = ob.oracle_diagonalize(A, 1, True, 0)           # max_num_sweeps = 0
+        ev0, vec0, it0 = run_gpu(A, 1, sweeps=0)
+        assert (it0 == 0).all() and np.array_equal(ev0, ref0[0]) and np.array_equal(vec0, ref0[1])
+
+
 def _random_symmetric(n, batch, dtype, seed):
     rng = np.random.default_rng(seed)            # (the counter generator stops at n = 256)
     A = rng.uniform(-1, 1, (batch, n, n))

@@ -134,3 +134,87 @@ def test_cluster_schedule_tables(n):
         for rank in range(4):
             cnt = sum(1 for K in range(128) if cl_owner(2 * K) == rank for L in range(K + 1, 128))
             assert cnt == 2032
+
+
+# ---- tier 3, block-ordering kernel (jpd_cta4.cuh): block odd-even sweep, tile storage, tile tables
+def block_sweep(m):
+    """Pairs met in one sweep of the block ordering (m a multiple of 4): the step inside the blocks,
+    then m/2 block steps A B A B ...; a block step on positions q0..q3 rotates (q0,q2)(q1,q3) with
+    exchange and (q0,q3)(q1,q2) without."""
+    pos = list(range(m))
+    met = []
+
+    def rot(p, q, exchange):
+        met.append((min(pos[p], pos[q]), max(pos[p], pos[q])))
+        if exchange:
+            pos[p], pos[q] = pos[q], pos[p]
+
+    for p in range(0, m, 2):
+        rot(p, p + 1, False)
+    nb = m // 2
+    for bs in range(nb):
+        for J in range(bs % 2, nb - 1, 2):
+            q0 = 2 * J
+            rot(q0, q0 + 2, True); rot(q0 + 1, q0 + 3, True)
+            rot(q0, q0 + 3, False); rot(q0 + 1, q0 + 2, False)
+    return met, pos
+
+
+@pytest.mark.parametrize("m", list(range(4, 132, 4)))
+def test_block_ordering_meets_every_pair_once_and_reverses_the_blocks(m):
+    met, pos = block_sweep(m)
+    assert sorted(met) == sorted(itertools.combinations(range(m), 2))
+    nb = m // 2
+    # the kernel's orig_index(): position p holds index 2 (nb-1 - p/2) + (p&1) after an odd number of sweeps
+    assert pos == [2 * (nb - 1 - (p >> 1)) + (p & 1) for p in range(m)]
+
+
+def cta4_shape(NPB):
+    kbp = NPB // 4
+    return dict(kbp=kbp, kw=((kbp + 15) // 16) * 16 + 1, threads=NPB * NPB // 32, kit=2)
+
+
+def tile4_off(off, w, r, c):
+    if off == 0:
+        return 4 * r + c
+    return (w * 17 if r >= 2 else 0) + (17 if c >= 2 else 0) + 4 * ((r + 2) & 3) + ((c + 2) & 3)
+
+
+@pytest.mark.parametrize("NPB", [64, 96, 128])
+def test_cta4_tile_storage_and_tables(NPB):
+    sh = cta4_shape(NPB)
+    w = sh["kw"]
+    addr = lambda i, j: ((i >> 2) * w + (j >> 2)) * 17 + 4 * (i & 3) + (j & 3)
+    for n in range(NPB - 31, NPB + 1):
+        m = (n + 3) & ~3
+        nbp = m // 4
+        # storage: distinct offsets for the upper triangle, inside the reserved area
+        offs = [addr(i, j) for i in range(m) for j in range(i, m)]
+        assert len(set(offs)) == len(offs) and max(offs) < sh["kbp"] * w * 17
+        for pat, np_ in ((0, nbp), (1, nbp - 1)):
+            off = 2 * pat
+            tbl = {}
+            for cl in range(16):
+                slot = 0
+                for P in range(np_):
+                    Q = P + 1 + ((cl - 2 * P - 1) & 15)
+                    while Q < np_:
+                        idx = (slot // (sh["threads"] // 16)) * sh["threads"] + (slot % (sh["threads"] // 16)) * 16 + cl
+                        assert idx < sh["kit"] * sh["threads"], "tile table overflow: a tile would be dropped"
+                        assert idx not in tbl
+                        tbl[idx] = (P, Q)
+                        slot += 1
+                        Q += 16
+            assert sorted(tbl.values()) == sorted(itertools.combinations(range(np_), 2))
+            # the 16 elements of a pattern-OFF tile are the elements the ordering says, in the stored triangle
+            for P, Q in tbl.values():
+                for r in range(4):
+                    for c in range(4):
+                        assert (P * w + Q) * 17 + tile4_off(off, w, r, c) == addr(4 * P + off + r, 4 * Q + off + c)
+            # every half warp of an iteration touches 16 different 8-byte banks, whatever the element
+            for it in range(sh["kit"]):
+                for hw in range(sh["threads"] // 16):
+                    base = it * sh["threads"] + hw * 16
+                    ids = [tbl[base + l][0] * w + tbl[base + l][1] for l in range(16) if base + l in tbl]
+                    banks = [(i * 17) % 16 for i in ids]
+                    assert len(set(banks)) == len(banks)
