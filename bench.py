@@ -342,6 +342,7 @@ SIDE_CASES = (
     (32, "float64", 1 << 18, "aos", 2, 1000, 1 << 12),
     (32, "float32", 1 << 18, "aos", 2, 1000, 0),
     (128, "float64", 8192, "aos", 1, 32, 0),                 # configs[3]
+    (128, "float32", 8192, "aos", 1, 32, 0),                 # same shape in fp32 (context: the tier-3 block-ordering kernel)
     (256, "float64", 2048, "aos", 1, 8, 64),
     (4, "float64", 1 << 22, "soa", 3, 0, 1 << 16),            # cuSOLVER column for the headline shape
     (512, "float64", 64, "aos", 1, 16, 0),                   # beyond the configs: reference benchmarks to n = 1000
