@@ -634,6 +634,26 @@ def run_own_arm(args):
                      "frac_of_pcie_copy_bound": (eb * world * e2e_steps / dtf / fused_bound) if fused_bound else None}
         del h_corr, h_lam, h_quat, h_it
 
+        # ---- the metric's other sizes end to end (pinned AoS host buffers through the same host entry)
+        for mn, mb in ((3, 1 << 23), (32, 1 << 17)):
+            hm = torch.empty((mb, mn, mn), dtype=torch.float64).pin_memory()
+            hev = torch.empty((mb, mn), dtype=torch.float64).pin_memory()
+            hvec = torch.empty((mb, mn, mn), dtype=torch.float64).pin_memory()
+            hit = torch.empty((mb,), dtype=torch.int32).pin_memory()
+            tmp = torch.empty((mb, mn, mn), dtype=torch.float64, device="cuda")
+            jpd.fill_synthetic(tmp, mn, mb, jpd.LAYOUT_AOS, 0, 1234, b0=rank * mb)
+            hm.copy_(tmp); del tmp
+            torch.cuda.synchronize()
+            msteps = max(1, min(e2e_steps, 3))
+            dts = timed_host(lambda: jpd.diagonalize_batched_host(hm, hev, hvec, hit, mn, mb, jpd.LAYOUT_AOS, SORT_DEC, True,
+                                                                  MAX_SWEEPS, device=local_rank), msteps)
+            metric_sizes[f"n{mn}_fp64"]["e2e"] = {
+                "value": mb * world * msteps / dts, "unit": "matrices/s", "steps": msteps,
+                "h2d_bytes_per_step": int(hm.numel() * 8),
+                "d2h_bytes_per_step": int(hev.numel() * 8 + hvec.numel() * 8 + hit.numel() * 4),
+                "failed_rank0": int((hit == 0).sum().item())}
+            del hm, hev, hvec, hit
+
     line = None
     if rank == 0:
         line = {
