@@ -242,7 +242,7 @@ __global__ void blk_count_kernel(const int* __restrict__ piv_iters, int npairs, 
   int rot = 0;
   for (int k = 0; k < npairs; ++k) {
     const int it = piv_iters[lb * npairs + k];
-    rot += it > 0 ? it - 1 : 1 << 16;      // an unfinished inner solve certainly rotated
+    rot += it > 0 ? it - 1 : (it < 0 ? -it - 1 : 1 << 16);   // < 0: a capped inner solve, -(rotations + 1): it certainly rotated
   }
   if (rot) {
     rot_total[lb] = min(rot_total[lb] + rot, 0x3fffffff);

@@ -344,6 +344,9 @@ jpd_cta4_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict_
                 int* __restrict__ n_iters, int n, long long batch, int soa, int sort_criteria,
                 int max_num_sweeps) {
   using Sh = Cta4Shape<NPB>;
+  // internal callers (tier 5's capped pivot solves) pass -(cap): an unfinished solve then reports -(rotations + 1)
+  const bool raw_count = max_num_sweeps < 0;
+  if (raw_count) max_num_sweeps = -max_num_sweeps;
   using T2 = typename Pair2<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
@@ -487,7 +490,7 @@ jpd_cta4_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict_
       if (soa) evals[(size_t)tid * (size_t)batch + (size_t)b] = val;
       else evals[(size_t)b * n + tid] = val;
     }
-    if (tid == 0 && n_iters) n_iters[b] = converged ? *rot_total + 1 : 0;
+    if (tid == 0 && n_iters) n_iters[b] = converged ? *rot_total + 1 : (raw_count ? -(*rot_total + 1) : 0);
     if (EVECS) {
       T* Es = M;
 #pragma unroll

@@ -27,12 +27,16 @@ void block_pairs(int nb, int step, std::vector<int2>& out) {
   }
 }
 
-// inner sweeps of a pivot solve: full convergence of every 64 x 64 block is not needed for the
-// outer iteration to converge (quadratically); JPD_BLOCK_INNER_SWEEPS overrides (tuning aid)
+// Inner sweeps of a pivot solve.  Full convergence of every 64 x 64 block is not needed for the outer
+// iteration to converge quadratically: measured on B200 (tests/scratch/t5inner.py), a cap of 2 inner
+// sweeps gives the same accuracy and outer sweep count + 1 at 1.25x-1.28x the speed of full inner
+// convergence (n = 300: 1436 -> 1845 matrices/s, 512: 435 -> 544, 1000: 53.9 -> 68.3).  The cap is
+// passed as a NEGATIVE sweep budget, which makes an unfinished solve report -(rotations + 1) instead of
+// 0, so the rotation count stays a count.  JPD_BLOCK_INNER_SWEEPS overrides (tuning aid).
 int inner_sweeps() {
   static int v = -1;
   if (v < 0) {
-    v = 50;
+    v = 2;
     if (const char* env = std::getenv("JPD_BLOCK_INNER_SWEEPS")) {
       const long x = std::strtol(env, nullptr, 10);
       if (x >= 1 && x <= 50) v = (int)x;
@@ -111,7 +115,7 @@ int launch_block(const T* mat, T* evals, T* evecs, int* iters, int n, long long 
         // never settles and block Jacobi converges only linearly (measured: n = 1000 not done
         // after 50 sweeps; sorted: 8 sweeps).  Sorted, Q tends to the identity.
         status = launch_tier3<T>(P, pev, Q, piv_it, kBjPivot, (long long)npairs * cnt, JPD_LAYOUT_AOS,
-                                 JPD_SORT_DECREASING_EVALS, 1, inner_sweeps(), st);
+                                 JPD_SORT_DECREASING_EVALS, 1, -inner_sweeps(), st);
         if (status != JPD_OK) break;
         blk_orthonormalize_kernel<T><<<(unsigned)(npairs * cnt), kBjThreads, apply_smem, st>>>(Q);
         apply<<<dim3(items, (unsigned)cnt), kBjThreads, apply_smem, st>>>(Mw, Ew, Q, prs, npairs, np);
