@@ -21,13 +21,14 @@
 //  * M is stored tile-major, 17 elements per tile, tile (P,Q) at (P*W + Q)*17: threads that own
 //    consecutive tiles touch different banks in both patterns (pattern B's tiles straddle four
 //    stored tiles at compile-time offsets).
-//  * E (n x n) lives in registers, thread (v, ch) owns rows 32 ch .. 32 ch + 31 of column v, and
-//    is updated with SCALED ("fast") rotations: row p is kept as f_p * e~_p, a rotation costs 2
+//  * E (n x n) lives in registers, thread (vp, ech) owns rows 16 ech .. 16 ech + 15 of the TWO columns vp and
+//    vp + n/2 (so that every broadcast (alpha, beta) it fetches serves two columns: the fetches were the largest
+//    single item of shared-memory traffic with one column of 32 rows per thread), and is updated with SCALED ("fast") rotations: row p is kept as f_p * e~_p, a rotation costs 2
 //    FMAs per thread and pair instead of 2 multiplications + 2 FMAs (e~_p -= alpha e~_q,
 //    e~_q += beta e~_p, alpha = t f_q/f_p, beta = t f_p/f_q, f *= c).  The thread that owns the
 //    pivot keeps f and 1/f (1/c falls out of the rotation), and the scales are folded back into
 //    the rows once per sweep, so they stay within [2^-65, 1] and f * (1/f) within a few ulp of 1.
-//    In pattern B the block pair that straddles two 32-row chunks is rotated by both owners
+//    In pattern B the block pair that straddles two 16-row chunks is rotated by both owners
 //    (each receives the other's two rows through a small shared buffer).
 //  * The eigenvector phase of a block step runs beside the pivot phase of the next one (the
 //    pivots occupy one warp); (alpha, beta) are double-buffered.
@@ -46,8 +47,10 @@ template <int NPB> struct Cta4Shape {
   static constexpr int kTileStride = 17;                // 16 + 1: consecutive tiles start in consecutive banks
   static constexpr int kMElems = ((kBP * kW * kTileStride + 1) / 2) * 2 > NPB * NPB ? ((kBP * kW * kTileStride + 1) / 2) * 2 : NPB * NPB;
   static constexpr int kCs = 5;                         // (c,s) slots per block pair (4 used; 16-byte bank groups (5J+k) mod 8)
+  static constexpr int kERows = 16;                     // E: a thread owns rows 16 ech .. 16 ech + 15 of the two columns vp, vp + NPB/2
+  static constexpr int kEChunks = NPB / kERows;
   // elements of T:  M | (c,s) | (alpha,beta) x2 | (f,1/f) | evals | boundary rows lo, hi
-  static constexpr int kElems = kMElems + 2 * kCs * kBP + 2 * 2 * kCs * kBP + 2 * NPB + NPB + 2 * 2 * kChunks * NPB;
+  static constexpr int kElems = kMElems + 2 * kCs * kBP + 2 * 2 * kCs * kBP + 2 * NPB + NPB + 2 * 2 * kEChunks * NPB;
   static constexpr int kHalfWarps = kThreads / 16;
   static constexpr int kIt = 2;                         // tile slots per thread and pattern (the second one is rarely used)
   JPD_CX static constexpr size_t table_bytes() { return (size_t)2 * kIt * kThreads * sizeof(unsigned); }
@@ -122,17 +125,16 @@ JPD_HD void scale_update4(T& fp, T& fq, T& rfp, T& rfq, T c, T t, T u, T& alpha,
   fp = EX ? nfq : nfp; fq = EX ? nfp : nfq;
   rfp = EX ? nrq : nrp; rfq = EX ? nrp : nrq;
 }
-// the four scaled rotations of a block step on rows x0..x3 (positions q0..q3); h = (alpha, beta) x 4
+// the four scaled rotations of a block step on rows x0..x3 (positions q0..q3); h0..h3 = (alpha, beta) of the
+// step's rotations (the inner step uses two)
 template <typename T, typename T2, int MODE>
-JPD_HD void fast_rotate_group(T& x0, T& x1, T& x2, T& x3, const T2* h) {
+JPD_HD void fast_rotate_group(T& x0, T& x1, T& x2, T& x3, T2 h0, T2 h1, T2 h2, T2 h3) {
   if (MODE != 2) {
-    const T2 h0 = h[0], h1 = h[1], h2 = h[2], h3 = h[3];
     fast_rotate_rows<T, true>(x0, x2, h0.x, h0.y);
     fast_rotate_rows<T, true>(x1, x3, h1.x, h1.y);
     fast_rotate_rows<T, false>(x0, x3, h2.x, h2.y);
     fast_rotate_rows<T, false>(x1, x2, h3.x, h3.y);
   } else {
-    const T2 h0 = h[0], h1 = h[1];
     fast_rotate_rows<T, false>(x0, x1, h0.x, h0.y);
     fast_rotate_rows<T, false>(x2, x3, h1.x, h1.y);
   }
@@ -144,7 +146,8 @@ template <typename T> struct Cta4Ctx {
   using T2 = typename Pair2<T>::type;
   T* M; T2* cs; T2* ab; T2* fr; T* xlo; T* xhi;
   const unsigned* tblA; const unsigned* tblB;
-  int m, nbp, v, ch;
+  int m, nbp, v, ch;      // v, ch: column / 32-row chunk of the convergence test
+  int c0, ech;            // E: first column (the second is c0 + NPB/2) and 16-row chunk
 };
 
 // MODE 0: block step of pattern A (block pairs at positions 4J..4J+3), 1: pattern B (4J+2..4J+5,
@@ -298,30 +301,64 @@ __device__ __forceinline__ void cta4_evecs(const Cta4Ctx<T>& cx, T (&e)[32]) {
   using Sh = Cta4Shape<NPB>;
   using T2 = typename Pair2<T>::type;
   constexpr int OFF = (MODE == 1) ? 2 : 0;
+  constexpr int kGroups = Sh::kERows / 4;     // block pairs per chunk
   const int npairs = (MODE == 1) ? cx.nbp - 1 : cx.nbp;
-  const int ch = cx.ch, v = cx.v;
+  const int ech = cx.ech;
   const T2* ab = cx.ab + ab_buffer(MODE) * Sh::kCs * Sh::kBP;
-  const int J0 = 8 * ch;    // block pair of this chunk's first four rows
-  T lo0 = e[0], lo1 = e[1], hi0 = e[30], hi1 = e[31];
+  const int J0 = kGroups * ech;    // block pair of this chunk's first four rows
   if (MODE == 1) {
     // the block pairs that straddle a chunk boundary: both owners rotate all four rows
-    if (ch > 0 && J0 - 1 < npairs) {
-      T y0 = cx.xhi[(2 * (ch - 1) + 0) * NPB + v], y1 = cx.xhi[(2 * (ch - 1) + 1) * NPB + v];
-      fast_rotate_group<T, T2, MODE>(y0, y1, lo0, lo1, ab + Sh::kCs * (J0 - 1));
+    if (ech > 0 && J0 - 1 < npairs) {
+      const T2* h = ab + Sh::kCs * (J0 - 1);
+      const T2 h0 = h[0], h1 = h[1], h2 = h[2], h3 = h[3];
+#pragma unroll
+      for (int col = 0; col < 2; ++col) {
+        const int c = cx.c0 + col * (NPB / 2), cb = Sh::kERows * col;
+        T y0 = cx.xhi[(2 * (ech - 1) + 0) * NPB + c], y1 = cx.xhi[(2 * (ech - 1) + 1) * NPB + c];
+        T lo0 = e[cb], lo1 = e[cb + 1];
+        fast_rotate_group<T, T2, MODE>(y0, y1, lo0, lo1, h0, h1, h2, h3);
+        // (the interior groups below do not touch rows 0, 1, 14, 15 in this pattern)
+        e[cb] = lo0; e[cb + 1] = lo1;
+      }
     }
-    if (ch < Sh::kChunks - 1 && J0 + 7 < npairs) {
-      T y2 = cx.xlo[(2 * (ch + 1) + 0) * NPB + v], y3 = cx.xlo[(2 * (ch + 1) + 1) * NPB + v];
-      fast_rotate_group<T, T2, MODE>(hi0, hi1, y2, y3, ab + Sh::kCs * (J0 + 7));
+    if (ech < Sh::kEChunks - 1 && J0 + kGroups - 1 < npairs) {
+      const T2* h = ab + Sh::kCs * (J0 + kGroups - 1);
+      const T2 h0 = h[0], h1 = h[1], h2 = h[2], h3 = h[3];
+#pragma unroll
+      for (int col = 0; col < 2; ++col) {
+        const int c = cx.c0 + col * (NPB / 2), cb = Sh::kERows * col;
+        T y2 = cx.xlo[(2 * (ech + 1) + 0) * NPB + c], y3 = cx.xlo[(2 * (ech + 1) + 1) * NPB + c];
+        T hi0 = e[cb + 14], hi1 = e[cb + 15];
+        fast_rotate_group<T, T2, MODE>(hi0, hi1, y2, y3, h0, h1, h2, h3);
+        e[cb + 14] = hi0; e[cb + 15] = hi1;
+      }
     }
   }
 #pragma unroll
-  for (int jj = 0; jj < 8 - (MODE == 1 ? 1 : 0); ++jj) {
+  for (int jj = 0; jj < kGroups - (MODE == 1 ? 1 : 0); ++jj) {
     if (J0 + jj < npairs) {
+      const T2* h = ab + Sh::kCs * (J0 + jj);
+      const T2 h0 = h[0], h1 = h[1], h2 = (MODE != 2) ? h[2] : h[0], h3 = (MODE != 2) ? h[3] : h[1];
       const int p = 4 * jj + OFF;   // compile-time after unrolling
-      fast_rotate_group<T, T2, MODE>(e[p], e[p + 1], e[p + 2], e[p + 3], ab + Sh::kCs * (J0 + jj));
+#pragma unroll
+      for (int col = 0; col < 2; ++col) {
+        const int q = Sh::kERows * col + p;
+        fast_rotate_group<T, T2, MODE>(e[q], e[q + 1], e[q + 2], e[q + 3], h0, h1, h2, h3);
+      }
     }
   }
-  if (MODE == 1) { e[0] = lo0; e[1] = lo1; e[30] = hi0; e[31] = hi1; }
+}
+
+// the rows next to the chunk boundaries, published for the eigenvector phase of a pattern-B step
+template <typename T, int NPB>
+__device__ __forceinline__ void cta4_publish_rows(const Cta4Ctx<T>& cx, const T (&e)[32]) {
+  using Sh = Cta4Shape<NPB>;
+#pragma unroll
+  for (int col = 0; col < 2; ++col) {
+    const int c = cx.c0 + col * (NPB / 2), cb = Sh::kERows * col;
+    if (cx.ech > 0) { cx.xlo[(2 * cx.ech + 0) * NPB + c] = e[cb]; cx.xlo[(2 * cx.ech + 1) * NPB + c] = e[cb + 1]; }
+    if (cx.ech < Sh::kEChunks - 1) { cx.xhi[(2 * cx.ech + 0) * NPB + c] = e[cb + 14]; cx.xhi[(2 * cx.ech + 1) * NPB + c] = e[cb + 15]; }
+  }
 }
 
 // first phase of a block step: the pivots of this step (warp 0) beside the eigenvector phase of the previous one
@@ -331,10 +368,7 @@ __device__ __forceinline__ void cta4_front(const Cta4Ctx<T>& cx, T (&e)[EVECS ? 
   if (threadIdx.x < 32) cta4_diag<T, NPB, EVECS, MODE>(cx, n_rot);
   if constexpr (EVECS) {
     if constexpr (PREV >= 0) cta4_evecs<T, NPB, PREV>(cx, e);
-    if constexpr (MODE == 1) {   // publish the rows next to the chunk boundaries for this step's eigenvector phase
-      if (cx.ch > 0) { cx.xlo[(2 * cx.ch + 0) * NPB + cx.v] = e[0]; cx.xlo[(2 * cx.ch + 1) * NPB + cx.v] = e[1]; }
-      if (cx.ch < Sh::kChunks - 1) { cx.xhi[(2 * cx.ch + 0) * NPB + cx.v] = e[30]; cx.xhi[(2 * cx.ch + 1) * NPB + cx.v] = e[31]; }
-    }
+    if constexpr (MODE == 1) cta4_publish_rows<T, NPB>(cx, e);   // for this step's eigenvector phase
   }
 }
 
@@ -381,12 +415,13 @@ jpd_cta4_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict_
   T2* fr = ab + 2 * Sh::kCs * Sh::kBP;
   T* ev = reinterpret_cast<T*>(fr + NPB);
   T* xlo = ev + NPB;
-  T* xhi = xlo + 2 * Sh::kChunks * NPB;
+  T* xhi = xlo + 2 * Sh::kEChunks * NPB;
   int* perm = reinterpret_cast<int*>(smem_raw + Sh::table_bytes() + ((size_t)Sh::kElems * sizeof(T) + 15) / 16 * 16);
   int* rot_total = perm + NPB;
   Cta4Ctx<T> cx;
   cx.M = M; cx.cs = cs; cx.ab = ab; cx.fr = fr; cx.xlo = xlo; cx.xhi = xhi;
   cx.tblA = tblA; cx.tblB = tblB; cx.m = m; cx.nbp = nbp; cx.v = v; cx.ch = ch;
+  cx.c0 = tid % (NPB / 2); cx.ech = tid / (NPB / 2);
   __syncthreads();
 
   for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
@@ -405,7 +440,8 @@ jpd_cta4_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict_
     T e[EVECS ? 32 : 1];
     if (EVECS) {
 #pragma unroll
-      for (int k = 0; k < 32; ++k) e[k] = (32 * ch + k == v) ? T(1) : T(0);   // :172-178
+      for (int k = 0; k < 32; ++k)   // :172-178
+        e[k] = (Sh::kERows * cx.ech + (k & 15) == cx.c0 + (k >> 4) * (NPB / 2)) ? T(1) : T(0);
     }
     __syncthreads();
 
@@ -447,7 +483,7 @@ jpd_cta4_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict_
         cta4_evecs<T, NPB, 1>(cx, e);     // the last B step's eigenvector phase
         // fold the row scales back into the rows (keeps f and 1/f near 1)
 #pragma unroll
-        for (int k = 0; k < 32; ++k) e[k] *= fr[32 * ch + k].x;
+        for (int k = 0; k < Sh::kERows; ++k) { const T fk = fr[Sh::kERows * cx.ech + k].x; e[k] *= fk; e[Sh::kERows + k] *= fk; }
         __syncthreads();
         if (tid < NPB) { T2 one; one.x = T(1); one.y = T(1); fr[tid] = one; }
       }
@@ -494,7 +530,7 @@ jpd_cta4_kernel(const T* __restrict__ mat, T* __restrict__ evals, T* __restrict_
     if (EVECS) {
       T* Es = M;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) Es[(32 * ch + k) * NPB + v] = e[k];
+      for (int k = 0; k < 32; ++k) Es[(Sh::kERows * cx.ech + (k & 15)) * NPB + cx.c0 + (k >> 4) * (NPB / 2)] = e[k];
       __syncthreads();
       for (int idx = tid; idx < n * n; idx += Sh::kThreads) {
         const int k = idx / n, c = idx - k * n;
