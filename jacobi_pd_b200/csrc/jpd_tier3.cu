@@ -67,16 +67,20 @@ bool tier3_legacy() {
   static const bool v = [] { const char* e = std::getenv("JPD_TIER3_LEGACY"); return e && e[0] == '1'; }();
   return v;
 }
+bool tier3_force_block() {   // JPD_TIER3_LEGACY=0: the block-ordering kernel at every size (tuning of the switch points)
+  static const bool v = [] { const char* e = std::getenv("JPD_TIER3_LEGACY"); return e && e[0] == '0'; }();
+  return v;
+}
 
 }  // namespace
 
 template <typename T>
 int launch_tier3(JPD_TIER_ARGS(T)) {
-  // Measured on B200 (tests/scratch/t3sweep.py, DESIGN.md "tier 3"): the block-ordering kernel wins for
-  // fp32 at every size (1.2x-1.6x) and for fp64 at 53 <= n <= 64 and n >= 97 (1.03x-1.16x); for the
-  // other fp64 sizes the first-generation kernel keeps two (n <= 96) or four resident blocks per SM
-  // where the new one, with its 4x4 register tiles, fits fewer, and stays ahead.
-  const bool block_order = !tier3_legacy() && (sizeof(T) == 4 || n >= 97 || (n >= 53 && n <= 64));
+  // Measured on B200 (tests/scratch/t3sweep.py, t3sweep2.py; DESIGN.md "tier 3"): the block-ordering kernel wins
+  // for fp32 at every size (1.22x-1.71x) and for fp64 at 47 <= n <= 64 (1.02x-1.13x) and n >= 97 (1.17x-1.22x);
+  // for the other fp64 sizes the first-generation kernel keeps two (65..96) or four resident blocks per SM where
+  // the new one, with its 4x4 register tiles, fits fewer, and stays ahead by 3-17 %.
+  const bool block_order = !tier3_legacy() && (tier3_force_block() || sizeof(T) == 4 || n >= 97 || (n >= 47 && n <= 64));
   if (block_order) {
     if (n <= 64) return launch_cta4<T, 64>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
     if constexpr (sizeof(T) == 4) {
