@@ -561,15 +561,22 @@ def run_own_arm(args):
         h_mat.copy_(tmp); del tmp
         torch.cuda.synchronize()
 
-        def timed_host(fn, steps):
+        def timed_host(fn, steps, reps=2):
+            """wall clock of `steps` calls, max over ranks; the better of `reps` back-to-back measurements
+            (a host-side pipeline is exposed to scheduling noise of the box: one descheduled feeder thread
+            costs 20 % of a 0.3 s measurement)"""
             for _ in range(max(1, min(args.warmup, 2))):
                 fn()
-            barrier(); torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(steps):
-                fn()
-            torch.cuda.synchronize()
-            return max_over_ranks(time.perf_counter() - t0)
+            best = None
+            for _ in range(reps):
+                barrier(); torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    fn()
+                torch.cuda.synchronize()
+                dt_ = max_over_ranks(time.perf_counter() - t0)
+                best = dt_ if best is None else min(best, dt_)
+            return best
 
         def e2e_step():
             jpd.diagonalize_batched_host(h_mat, h_ev, h_vec, h_it, n, eb, jpd.LAYOUT_AOS, SORT_DEC, True,
@@ -601,7 +608,8 @@ def run_own_arm(args):
         e2e = {"value": eb * world * e2e_steps / dt, "unit": "matrices/s",
                "h2d_bytes_per_step": int(h_mat.numel() * 8),
                "d2h_bytes_per_step": int(h_ev.numel() * 8 + h_vec.numel() * 8 + h_it.numel() * 4),
-               "steps": e2e_steps, "batch_per_gpu": eb, "host_layout": "aos", "host_memory": "pinned",
+               "steps": e2e_steps, "timing": "wall clock of `steps` host calls, better of 2 measurements, max over ranks",
+               "batch_per_gpu": eb, "host_layout": "aos", "host_memory": "pinned",
                "checksum_evals": float(h_ev[:: max(1, eb // 4096)].sum().item()),
                "pcie_copy_bound": pcie_bound,
                "frac_of_pcie_copy_bound": (eb * world * e2e_steps / dt / pcie_bound) if pcie_bound else None}
