@@ -4,6 +4,8 @@
 
 #include "jpd_internal.h"
 #include "jpd_cluster.cuh"
+#include "jpd_cluster4.cuh"
+#include <cstdlib>
 
 namespace jpd_host {
 using namespace jpd;
@@ -42,10 +44,52 @@ int launch_cluster(const T* mat, T* evals, T* evecs, int* iters, int n, long lon
   return JPD_OK;
 }
 
+// block-ordering kernel on the cluster (jpd_cluster4.cuh)
+template <typename T>
+int launch_cluster4(const T* mat, T* evals, T* evecs, int* iters, int n, long long batch, int layout,
+                    int sort, int calc, int sweeps, cudaStream_t st) {
+  using Sh = Cl4Shape;
+  const size_t smem = Sh::block_bytes(sizeof(T));
+  auto kernel = calc ? jpd_cluster4_kernel<T, true> : jpd_cluster4_kernel<T, false>;
+  JPD_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int max_clusters = 0;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(Sh::kCtas * 64);
+    cfg.blockDim = dim3(Sh::kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = Sh::kCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess || max_clusters < 1) {
+      (void)cudaGetLastError();
+      max_clusters = 32;
+    }
+  }
+  const long long clusters = std::min<long long>(batch, max_clusters);
+  kernel<<<dim3((unsigned)(clusters * Sh::kCtas)), dim3(Sh::kThreads), smem, st>>>(
+      mat, evals, evecs, iters, n, batch, layout == JPD_LAYOUT_SOA ? 1 : 0, sort, sweeps);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  JPD_CK(cudaGetLastError());
+  return JPD_OK;
+}
+// development switches: JPD_TIER4_BLOCK=1 forces the block-ordering kernel at every size, =0 the first-generation one
+int tier4_switch() {
+  static const int v = [] { const char* e = std::getenv("JPD_TIER4_BLOCK"); return e ? (e[0] == '1' ? 1 : (e[0] == '0' ? 0 : -1)) : -1; }();
+  return v;
+}
+
 }  // namespace
 
 template <typename T>
 int launch_tier4(JPD_TIER_ARGS(T)) {
+  // Measured on B200 (tests/scratch/t4sweep.py; DESIGN.md "tier 4"): the block-ordering kernel is 1.53x-1.66x
+  // faster in fp32 at every size and 1.03x-1.07x in fp64 from n = 176 up; below that the first-generation
+  // kernel is ahead by 1-5 % in fp64.
+  const int sw = tier4_switch();
+  const bool block_order = sw == 1 || (sw != 0 && (sizeof(T) == 4 || n >= 176));
+  if (block_order) return launch_cluster4<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
   return launch_cluster<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
 }
 

@@ -99,6 +99,35 @@ def test_parity_tier3_both_kernels(n, dtype):
             assert all(np.array_equal(x, y) for x, y in zip(first, again))
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [131, 145, 175, 176, 177, 191, 193, 230, 253])
+def test_parity_tier4_both_kernels(n, dtype):
+    """tier 4 dispatches between the first-generation cluster kernel and the block-ordering one (jpd_cluster4.cuh:
+    4x4 register tiles, tile rows dealt to the four CTAs in groups of eight, pattern-B tiles that reach into a
+    neighbour CTA) by size and precision: both sides of the switch point, every padding, tile rows on either side
+    of a group boundary, all sort criteria and the no-eigenvector path on two of them, bit-repeatability"""
+    A = ob.fill_synthetic(n, 5, seed=5000 + n, dtype=dtype)
+    ref = ob.oracle_diagonalize(A, 1)
+    for layout in (0, 1):
+        out = run_gpu(A, 1, layout=layout)
+        parity.full_check(A, out, ref, 1)
+    if n in (177, 253):
+        for sort in (0, 2, 3, 4):
+            parity.full_check(A, run_gpu(A, sort), ob.oracle_diagonalize(A, sort), sort)
+        ev, vec, it = run_gpu(A, 1, calc=False)
+        assert vec is None
+        parity.check_evals(ev, ref[0])
+        ref0 = ob.oracle_diagonalize(A, 1, True, 0)           # max_num_sweeps = 0
+        ev0, vec0, it0 = run_gpu(A, 1, sweeps=0)
+        assert (it0 == 0).all() and np.array_equal(ev0, ref0[0]) and np.array_equal(vec0, ref0[1])
+        big = ob.fill_synthetic(n, 70, seed=5100 + n, dtype=dtype)   # more matrices than resident clusters
+        first = run_gpu(big, 1)
+        for _ in range(2):
+            again = run_gpu(big, 1)
+            assert all(np.array_equal(x, y) for x, y in zip(first, again))
+        parity.full_check(big, first, ob.oracle_diagonalize(big, 1), 1)
+
+
 def _random_symmetric(n, batch, dtype, seed):
     rng = np.random.default_rng(seed)            # (the counter generator stops at n = 256)
     A = rng.uniform(-1, 1, (batch, n, n))

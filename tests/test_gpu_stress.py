@@ -101,7 +101,7 @@ def test_structured_inputs(n, dtype):
     assert np.array_equal(ev0, ref0[0])
 
 
-@pytest.mark.parametrize("n", [2, 4, 6, 8, 12, 16, 24, 32, 40, 58, 100, 130])
+@pytest.mark.parametrize("n", [2, 4, 6, 8, 12, 16, 24, 32, 40, 58, 100, 130, 200])
 def test_nan_and_inf_inputs_terminate_and_do_not_disturb_their_neighbours(n):
     """NaN / Inf entries: the matrix is reported as not converged (n_iters == 0, DESIGN.md
     deviation 5) after max_num_sweeps sweeps; matrices that share its warp / block (tier 2
