@@ -84,11 +84,12 @@ int tier4_switch() {
 
 template <typename T>
 int launch_tier4(JPD_TIER_ARGS(T)) {
-  // Measured on B200 (tests/scratch/t4sweep.py; DESIGN.md "tier 4"): the block-ordering kernel is 1.53x-1.66x
-  // faster in fp32 at every size and 1.03x-1.07x in fp64 from n = 176 up; below that the first-generation
-  // kernel is ahead by 1-5 % in fp64.
+  // Measured on B200 (tests/scratch/t4sweep.py; DESIGN.md "tier 4"): since its pivots travel as bulk copies
+  // (jpd_cluster4.cuh) the block-ordering kernel is ahead at every size and in both precisions -- 264 matrices,
+  // fp64: n = 129 14.3 ms against 17.2 ms, n = 256 36.3 against 50.3; fp32: 9.1 against 14.5, 23.8 against 39.3.
+  // The first-generation kernel stays for JPD_TIER4_BLOCK=0 (tests run both).
   const int sw = tier4_switch();
-  const bool block_order = sw == 1 || (sw != 0 && (sizeof(T) == 4 || n >= 176));
+  const bool block_order = sw != 0;
   if (block_order) return launch_cluster4<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
   return launch_cluster<T>(mat, evals, evecs, iters, n, batch, layout, sort, calc, sweeps, st);
 }

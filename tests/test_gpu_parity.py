@@ -102,10 +102,11 @@ def test_parity_tier3_both_kernels(n, dtype):
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("n", [131, 145, 175, 176, 177, 191, 193, 230, 253])
 def test_parity_tier4_both_kernels(n, dtype):
-    """tier 4 dispatches between the first-generation cluster kernel and the block-ordering one (jpd_cluster4.cuh:
-    4x4 register tiles, tile rows dealt to the four CTAs in groups of eight, pattern-B tiles that reach into a
-    neighbour CTA) by size and precision: both sides of the switch point, every padding, tile rows on either side
-    of a group boundary, all sort criteria and the no-eigenvector path on two of them, bit-repeatability"""
+    """tier 4 runs the block-ordering cluster kernel (jpd_cluster4.cuh: 4x4 register tiles, tile rows dealt to the
+    four CTAs in groups of eight, pattern-B tiles that reach into a neighbour CTA, pivots exchanged as bulk copies
+    on mbarriers): every padding, tile rows on either side of a group boundary, all sort criteria and the
+    no-eigenvector path on two of them, bit-repeatability (the name dates from the size-dependent dispatch of the
+    two tier-4 kernels; the first-generation one is covered by test_tier4_first_generation_kernel)"""
     A = ob.fill_synthetic(n, 5, seed=5000 + n, dtype=dtype)
     ref = ob.oracle_diagonalize(A, 1)
     for layout in (0, 1):
@@ -126,6 +127,25 @@ def test_parity_tier4_both_kernels(n, dtype):
             again = run_gpu(big, 1)
             assert all(np.array_equal(x, y) for x, y in zip(first, again))
         parity.full_check(big, first, ob.oracle_diagonalize(big, 1), 1)
+
+
+def test_tier4_first_generation_kernel():
+    """JPD_TIER4_BLOCK=0 selects the first-generation cluster kernel (jpd_cluster.cuh); the switch is read once per
+    process, hence the child process"""
+    import os, subprocess, sys
+    code = (
+        "import sys; sys.path.insert(0, 'tests'); sys.path.insert(0, '.')\n"
+        "import numpy as np, parity\n"
+        "from oracle import binding as ob\n"
+        "from gpu_util import run_gpu\n"
+        "for n, dt in ((200, np.float64), (131, np.float32)):\n"
+        "    A = ob.fill_synthetic(n, 5, seed=5200 + n, dtype=dt)\n"
+        "    parity.full_check(A, run_gpu(A, 1), ob.oracle_diagonalize(A, 1), 1)\n"
+        "print('ok')\n")
+    env = dict(os.environ, JPD_TIER4_BLOCK="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stdout + res.stderr
 
 
 def _random_symmetric(n, batch, dtype, seed):
