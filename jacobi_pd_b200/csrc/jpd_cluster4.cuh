@@ -388,11 +388,10 @@ __device__ __forceinline__ void cl4_evecs(const Cl4Ctx<T>& cx, T (&e)[32]) {
       for (int col = 0; col < 2; ++col) {
         const int c = cx.c0 + col * (Sh::kN / 2), cb = Sh::kERows * col;
         T y0, y1;
-        if (ech > 0) { y0 = cx.xhi()[(2 * (ech - 1) + 0) * Sh::kN + c]; y1 = cx.xhi()[(2 * (ech - 1) + 1) * Sh::kN + c]; }
-        else {
-          const unsigned a = cluster_map(cx.xhi_u32() + (unsigned)(((2 * 3 + 0) * Sh::kN + c) * esz), (unsigned)(cx.rank - 1));
-          y0 = ld_cluster(a, T(0)); y1 = ld_cluster(a + (unsigned)(Sh::kN * esz), T(0));
-        }
+        // chunk below: slot ech - 1; for ech == 0 it is the top chunk of CTA rank - 1, which PUSHED its rows into
+        // this CTA's slot 3 (cl4_back) -- a local load here instead of a round trip to the neighbour
+        const int below = (ech + 3) & 3;
+        y0 = cx.xhi()[(2 * below + 0) * Sh::kN + c]; y1 = cx.xhi()[(2 * below + 1) * Sh::kN + c];
         T lo0 = e[cb], lo1 = e[cb + 1];
         fast_rotate_group<T, T2, MODE>(y0, y1, lo0, lo1, h0, h1, h2, h3);
         e[cb] = lo0; e[cb + 1] = lo1;
@@ -405,11 +404,8 @@ __device__ __forceinline__ void cl4_evecs(const Cl4Ctx<T>& cx, T (&e)[32]) {
       for (int col = 0; col < 2; ++col) {
         const int c = cx.c0 + col * (Sh::kN / 2), cb = Sh::kERows * col;
         T y2, y3;
-        if (ech < 3) { y2 = cx.xlo()[(2 * (ech + 1) + 0) * Sh::kN + c]; y3 = cx.xlo()[(2 * (ech + 1) + 1) * Sh::kN + c]; }
-        else {
-          const unsigned a = cluster_map(cx.xlo_u32() + (unsigned)(((2 * 0 + 0) * Sh::kN + c) * esz), (unsigned)(cx.rank + 1));
-          y2 = ld_cluster(a, T(0)); y3 = ld_cluster(a + (unsigned)(Sh::kN * esz), T(0));
-        }
+        const int above = (ech + 1) & 3;                       // for ech == 3: pushed by the bottom chunk of CTA rank + 1
+        y2 = cx.xlo()[(2 * above + 0) * Sh::kN + c]; y3 = cx.xlo()[(2 * above + 1) * Sh::kN + c];
         T hi0 = e[cb + 14], hi1 = e[cb + 15];
         fast_rotate_group<T, T2, MODE>(hi0, hi1, y2, y3, h0, h1, h2, h3);
         e[cb + 14] = hi0; e[cb + 15] = hi1;
@@ -493,8 +489,27 @@ __device__ __forceinline__ void cl4_back(const Cl4Ctx<T>& cx, T (&e)[EVECS ? 32 
 #pragma unroll
           for (int col = 0; col < 2; ++col) {
             const int c = cx.c0 + col * (Sh::kN / 2), cb = Sh::kERows * col;
-            cx.xlo()[(2 * cx.ech + 0) * Sh::kN + c] = e[cb]; cx.xlo()[(2 * cx.ech + 1) * Sh::kN + c] = e[cb + 1];
-            cx.xhi()[(2 * cx.ech + 0) * Sh::kN + c] = e[cb + 14]; cx.xhi()[(2 * cx.ech + 1) * Sh::kN + c] = e[cb + 15];
+            // slot ech of this CTA -- except the rows a NEIGHBOUR CTA needs: the bottom chunk pushes its first two
+            // rows into slot 0 of CTA rank - 1, the top chunk its last two into slot 3 of CTA rank + 1 (four remote
+            // stores here instead of four remote loads, with their round trip, in the pattern-B step)
+            constexpr int esz = (int)sizeof(T);
+            const unsigned lo = (unsigned)(((2 * cx.ech + 0) * Sh::kN + c) * esz), hi = lo;
+            if (cx.ech == 0) {
+              if (cx.rank > 0) {
+                const unsigned a = cluster_map(cx.xlo_u32() + lo, (unsigned)(cx.rank - 1));
+                st_cluster(a, e[cb]); st_cluster(a + (unsigned)(Sh::kN * esz), e[cb + 1]);
+              }
+            } else {
+              cx.xlo()[(2 * cx.ech + 0) * Sh::kN + c] = e[cb]; cx.xlo()[(2 * cx.ech + 1) * Sh::kN + c] = e[cb + 1];
+            }
+            if (cx.ech == 3) {
+              if (cx.rank < 3) {
+                const unsigned a = cluster_map(cx.xhi_u32() + hi, (unsigned)(cx.rank + 1));
+                st_cluster(a, e[cb + 14]); st_cluster(a + (unsigned)(Sh::kN * esz), e[cb + 15]);
+              }
+            } else {
+              cx.xhi()[(2 * cx.ech + 0) * Sh::kN + c] = e[cb + 14]; cx.xhi()[(2 * cx.ech + 1) * Sh::kN + c] = e[cb + 15];
+            }
           }
         }
       }

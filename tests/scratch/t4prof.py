@@ -25,7 +25,7 @@ for path in sys.argv[1:]:
         buf = (ctypes.c_longlong * (4 * 16 * 8 + 16))()
         l.jpd_debug_cl4_prof(buf)
         steps = 64 * 10
-        print("  rank warp | A: front exch back bar2 | B: front exch back bar2   (cycles per block step, 10 sweeps assumed)")
+        print("  rank warp | A: front exch [back bar2 | or tiles evecs] B: ...   (cycles per block step, 10 sweeps assumed)")
         for r in range(4):
             for w in (0, 1, 2, 5, 15):
                 a = [buf[(r * 16 + w) * 8 + k] / steps for k in range(8)]
