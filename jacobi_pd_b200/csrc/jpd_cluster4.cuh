@@ -429,7 +429,8 @@ __device__ __forceinline__ void cl4_evecs(const Cl4Ctx<T>& cx, T (&e)[32]) {
 
 // first phase of a block step: the pivots this CTA owns (16 threads of warp 0).  The eigenvector rotations of a
 // step run in its SECOND phase, beside the tiles (cl4_back): measured with clock64 (tests/scratch/t4prof.py), the
-// pivot chain is slowed threefold when the other warps of its scheduler do eigenvector work at the same time, and
+// pivot chain takes 1.4 times longer (1990 against 1410 cycles) when the other warps of its scheduler do eigenvector
+// work at the same time, and
 // the pivot warp's own eigenvector work then follows it on the critical path.
 template <typename T, bool EVECS, int MODE>
 __device__ __forceinline__ void cl4_front(const Cl4Ctx<T>& cx) {
