@@ -218,3 +218,94 @@ def test_cta4_tile_storage_and_tables(NPB):
                     ids = [tbl[base + l][0] * w + tbl[base + l][1] for l in range(16) if base + l in tbl]
                     banks = [(i * 17) % 16 for i in ids]
                     assert len(set(banks)) == len(banks)
+
+
+# ---- tier 4, block-ordering kernel (jpd_cluster4.cuh): tile rows dealt in groups of eight, tile tables with the
+# straddling rows first, the two record ranges a CTA sends, the strips of pattern B
+def _cl4_owner_row(P):
+    g = P >> 3
+    return g if g < 4 else 7 - g
+
+
+def _cl4_local_row(P):
+    return (0 if (P >> 3) < 4 else 8) + (P & 7)
+
+
+def _cl4_global_row(l, rank):
+    return 8 * rank + l if l < 8 else 8 * (7 - rank) + (l - 8)
+
+
+def test_cluster4_ownership_and_record_ranges():
+    for P in range(64):
+        r, l = _cl4_owner_row(P), _cl4_local_row(P)
+        assert 0 <= r < 4 and 0 <= l < 16 and _cl4_global_row(l, r) == P
+    # the two contiguous ranges of pivot records a CTA sends (cl4_front): every block pair exactly once over the CTAs,
+    # each range = the pairs of pivot threads 0..7 / 8..15 of that CTA
+    seen = []
+    for rank in range(4):
+        for J0 in (8 * rank, 8 * (7 - rank)):
+            rng = list(range(J0, J0 + 8))
+            assert all(_cl4_owner_row(J) == rank for J in rng)
+            seen += rng
+        assert sorted(_cl4_global_row(l, rank) for l in range(16)) == sorted(seen[-16:])
+    assert sorted(seen) == list(range(64))
+    # the scales of position p live with the owner of tile row p / 4: a pattern-B pair J reads positions 4J+2 .. 4J+5,
+    # the last two of which are remote exactly when tile row J + 1 belongs to another CTA
+    for J in range(63):
+        remote = _cl4_owner_row(J + 1) != _cl4_owner_row(J)
+        owners = [_cl4_owner_row(p >> 2) for p in range(4 * J + 2, 4 * J + 6)]
+        assert owners[:2] == [_cl4_owner_row(J)] * 2 and (owners[2] != owners[0]) == remote and owners[2] == owners[3]
+
+
+@pytest.mark.parametrize("n", [129, 130, 176, 200, 253, 256])
+def test_cluster4_tile_tables_and_strips(n):
+    m = (n + 3) & ~3
+    nbp = m // 4
+    W, threads = 65, 512
+    for pat, np_ in ((0, nbp), (1, nbp - 1)):
+        all_tiles = []
+        for rank in range(4):
+            tbl, overflow = {}, []
+            for cl in range(16):
+                slot = 0
+                for ll in range(32):                      # straddling tile rows first (jpd_cluster4.cuh, table builder)
+                    l = ll % 16
+                    P = _cl4_global_row(l, rank)
+                    if P >= np_:
+                        continue
+                    remote = pat == 1 and _cl4_owner_row(P + 1) != rank
+                    if (ll < 16) != remote:
+                        continue
+                    Q = P + 1 + ((cl - l - P - 1) & 15)
+                    while Q < np_:
+                        assert (l + Q) % 16 == cl
+                        if slot < threads // 16:
+                            tbl[slot * 16 + cl] = (P, Q, remote)
+                            slot += 1
+                        else:
+                            overflow.append((P, Q, remote))
+                        Q += 16
+            free = [t for t in range(threads) if t not in tbl]
+            assert len(overflow) <= len(free), "a tile would be dropped"
+            for t, ent in zip(free, overflow):
+                tbl[t] = ent
+            all_tiles += [(P, Q) for P, Q, _ in tbl.values()]
+            # straddling tiles sit in the first warps: with at most four per bank class they stay below thread 64 + 16
+            strad = [t for t, (_, _, rem) in tbl.items() if rem]
+            if strad:
+                assert max(strad) < 16 * (max(sum(1 for t in strad if t % 16 == cl) for cl in range(16)))
+            # a half warp touches 16 different 8-byte banks (class-assigned entries)
+            for hw in range(threads // 16):
+                ids = [_cl4_local_row(tbl[hw * 16 + k][0]) * W + tbl[hw * 16 + k][1] for k in range(16)
+                       if hw * 16 + k in tbl and (_cl4_local_row(tbl[hw * 16 + k][0]) + tbl[hw * 16 + k][1]) % 16 == k]
+                assert len({(i * 17) % 16 for i in ids}) == len(ids)
+        assert sorted(all_tiles) == sorted(itertools.combinations(range(np_), 2))
+    # pattern-B strips: 64 top strips on lanes 0..3 of the 16 warps, 16 right strips on the last half warp
+    strips = {}
+    for tid in range(threads):
+        lane, warp = tid & 31, tid >> 5
+        r = warp * 4 + lane if lane < 4 else (64 + tid - (threads - 16) if tid >= threads - 16 else None)
+        if r is not None:
+            assert r not in strips
+            strips[r] = tid
+    assert sorted(strips) == list(range(80))
