@@ -84,28 +84,6 @@ __device__ __forceinline__ void bulk_copy_to_peer(unsigned dst_cluster, unsigned
 
 // Everything in shared memory sits at a compile-time offset from M, so the context carries ONE pointer and one
 // shared-window address (the kernel runs at the 128-register cap; a dozen loop-invariant pointers spilled).
-// shared-memory load that must not be scheduled before `after` has been computed (a fake input operand)
-__device__ __forceinline__ double2 lds_after(const double2* p, double after) {
-  double2 v;
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)), "d"(after));
-  return v;
-}
-__device__ __forceinline__ double lds_after(const double* p, double after) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)), "d"(after));
-  return v;
-}
-__device__ __forceinline__ float lds_after(const float* p, float after) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((unsigned)__cvta_generic_to_shared(p)), "f"(after));
-  return v;
-}
-__device__ __forceinline__ float2 lds_after(const float2* p, float after) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)), "f"(after));
-  return v;
-}
-
 template <typename T> struct Cl4Ctx {
   using T2 = typename Pair2<T>::type;
   using Sh = Cl4Shape;

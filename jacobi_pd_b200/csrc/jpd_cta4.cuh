@@ -142,6 +142,28 @@ JPD_HD void fast_rotate_group(T& x0, T& x1, T& x2, T& x3, T2 h0, T2 h1, T2 h2, T
 
 #if defined(__CUDACC__)
 
+// shared-memory load that must not be scheduled before `after` has been computed (a fake input operand)
+__device__ __forceinline__ double2 lds_after(const double2* p, double after) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)), "d"(after));
+  return v;
+}
+__device__ __forceinline__ double lds_after(const double* p, double after) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)), "d"(after));
+  return v;
+}
+__device__ __forceinline__ float lds_after(const float* p, float after) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((unsigned)__cvta_generic_to_shared(p)), "f"(after));
+  return v;
+}
+__device__ __forceinline__ float2 lds_after(const float2* p, float after) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)), "f"(after));
+  return v;
+}
+
 template <typename T> struct Cta4Ctx {
   using T2 = typename Pair2<T>::type;
   T* M; T2* cs; T2* ab; T2* fr; T* xlo; T* xhi;
@@ -240,10 +262,36 @@ __device__ __forceinline__ void cta4_tiles(const Cta4Ctx<T>& cx) {
     T* B = cx.M + (ent & 0xfffffu);
     const T2* csP = cx.cs + Sh::kCs * ((ent >> 20) & 0x3fu);
     const T2* csQ = cx.cs + Sh::kCs * (ent >> 26);
-    T t00 = B[tile4_off<OFF, W>(0, 0)], t01 = B[tile4_off<OFF, W>(0, 1)], t02 = B[tile4_off<OFF, W>(0, 2)], t03 = B[tile4_off<OFF, W>(0, 3)];
-    T t10 = B[tile4_off<OFF, W>(1, 0)], t11 = B[tile4_off<OFF, W>(1, 1)], t12 = B[tile4_off<OFF, W>(1, 2)], t13 = B[tile4_off<OFF, W>(1, 3)];
-    T t20 = B[tile4_off<OFF, W>(2, 0)], t21 = B[tile4_off<OFF, W>(2, 1)], t22 = B[tile4_off<OFF, W>(2, 2)], t23 = B[tile4_off<OFF, W>(2, 3)];
-    T t30 = B[tile4_off<OFF, W>(3, 0)], t31 = B[tile4_off<OFF, W>(3, 1)], t32 = B[tile4_off<OFF, W>(3, 2)], t33 = B[tile4_off<OFF, W>(3, 3)];
+    T t00, t01, t02, t03, t10, t11, t12, t13, t20, t21, t22, t23, t30, t31, t32, t33;
+    if (MODE != 2 && sizeof(T) == 8) {
+      // fp64 runs at the register cap (64 registers of eigenvector rows): the entries and the (c,s) pairs are loaded
+      // group by group, each load pinned behind a result of the group before it (lds_after) -- with everything
+      // loaded up front ptxas keeps an eigenvector element in local memory (one LDL + STL per thread and step)
+#define JPD_L4(r, c, after) lds_after(B + tile4_off<OFF, W>(r, c), after)
+      const T2 p0 = csP[0], q0 = csQ[0];
+      t00 = B[tile4_off<OFF, W>(0, 0)]; t02 = B[tile4_off<OFF, W>(0, 2)]; t20 = B[tile4_off<OFF, W>(2, 0)]; t22 = B[tile4_off<OFF, W>(2, 2)];
+      rotate_block4<T, true>(t00, t02, t20, t22, p0.x, p0.y, q0.x, q0.y);
+      const T2 q1 = lds_after(csQ + 1, t00);
+      t01 = JPD_L4(0, 1, t00); t03 = JPD_L4(0, 3, t00); t21 = JPD_L4(2, 1, t00); t23 = JPD_L4(2, 3, t00);
+      rotate_block4<T, true>(t01, t03, t21, t23, p0.x, p0.y, q1.x, q1.y);
+      const T2 p1 = lds_after(csP + 1, t01);
+      t10 = JPD_L4(1, 0, t01); t12 = JPD_L4(1, 2, t01); t30 = JPD_L4(3, 0, t01); t32 = JPD_L4(3, 2, t01);
+      rotate_block4<T, true>(t10, t12, t30, t32, p1.x, p1.y, q0.x, q0.y);
+      t11 = JPD_L4(1, 1, t10); t13 = JPD_L4(1, 3, t10); t31 = JPD_L4(3, 1, t10); t33 = JPD_L4(3, 3, t10);
+      rotate_block4<T, true>(t11, t13, t31, t33, p1.x, p1.y, q1.x, q1.y);
+      const T2 p2 = lds_after(csP + 2, t11), q2 = lds_after(csQ + 2, t11);
+      rotate_block4<T, false>(t00, t03, t30, t33, p2.x, p2.y, q2.x, q2.y);
+      const T2 q3 = lds_after(csQ + 3, t00);
+      rotate_block4<T, false>(t01, t02, t31, t32, p2.x, p2.y, q3.x, q3.y);
+      const T2 p3 = lds_after(csP + 3, t01);
+      rotate_block4<T, false>(t10, t13, t20, t23, p3.x, p3.y, q2.x, q2.y);
+      rotate_block4<T, false>(t11, t12, t21, t22, p3.x, p3.y, q3.x, q3.y);
+#undef JPD_L4
+    } else {
+    t00 = B[tile4_off<OFF, W>(0, 0)]; t01 = B[tile4_off<OFF, W>(0, 1)]; t02 = B[tile4_off<OFF, W>(0, 2)]; t03 = B[tile4_off<OFF, W>(0, 3)];
+    t10 = B[tile4_off<OFF, W>(1, 0)]; t11 = B[tile4_off<OFF, W>(1, 1)]; t12 = B[tile4_off<OFF, W>(1, 2)]; t13 = B[tile4_off<OFF, W>(1, 3)];
+    t20 = B[tile4_off<OFF, W>(2, 0)]; t21 = B[tile4_off<OFF, W>(2, 1)]; t22 = B[tile4_off<OFF, W>(2, 2)]; t23 = B[tile4_off<OFF, W>(2, 3)];
+    t30 = B[tile4_off<OFF, W>(3, 0)]; t31 = B[tile4_off<OFF, W>(3, 1)]; t32 = B[tile4_off<OFF, W>(3, 2)]; t33 = B[tile4_off<OFF, W>(3, 3)];
     const T2 p0 = csP[0], p1 = csP[1], q0 = csQ[0], q1 = csQ[1];
     if (MODE != 2) {
       rotate_block4<T, true>(t00, t02, t20, t22, p0.x, p0.y, q0.x, q0.y);
@@ -260,6 +308,7 @@ __device__ __forceinline__ void cta4_tiles(const Cta4Ctx<T>& cx) {
       rotate_block4<T, false>(t02, t03, t12, t13, p0.x, p0.y, q1.x, q1.y);
       rotate_block4<T, false>(t20, t21, t30, t31, p1.x, p1.y, q0.x, q0.y);
       rotate_block4<T, false>(t22, t23, t32, t33, p1.x, p1.y, q1.x, q1.y);
+    }
     }
     B[tile4_off<OFF, W>(0, 0)] = t00; B[tile4_off<OFF, W>(0, 1)] = t01; B[tile4_off<OFF, W>(0, 2)] = t02; B[tile4_off<OFF, W>(0, 3)] = t03;
     B[tile4_off<OFF, W>(1, 0)] = t10; B[tile4_off<OFF, W>(1, 1)] = t11; B[tile4_off<OFF, W>(1, 2)] = t12; B[tile4_off<OFF, W>(1, 3)] = t13;
