@@ -13,15 +13,16 @@
 //    to the CTAs in groups of 8, group g to CTA g or 7-g, which gives every CTA exactly a quarter of
 //    the tiles of the upper triangle and makes a pattern-B tile -- it straddles two tile rows --
 //    reach into a neighbour CTA only once in eight (ld/st.shared::cluster for its lower half);
-//  * every CTA holds all (c,s), (alpha,beta) and row scales, so every read is local.  The 16 pivot threads of a
-//    CTA write their results into the CTA's own copy; one warp then sends the CTA's two contiguous ranges of each
-//    array to the three other CTAs as bulk copies (cp.async.bulk shared::cta -> shared::cluster) that complete on
-//    the RECEIVER's mbarrier, and every thread of the cluster waits on its own CTA's mbarrier instead of a cluster
-//    barrier.  (Measured with clock64, tests/scratch/t4prof.py: the 48 st.shared::cluster.v2 per pivot thread of
+//  * every CTA holds the pivot records -- (c,s) x4 and (alpha,beta) x4 -- of all 64 block pairs, so every read
+//    in the tile and eigenvector phases is local.  The 16 pivot threads of a CTA write their records into the
+//    CTA's own copy; warp 0 then sends the CTA's two contiguous ranges of records to the three other CTAs as bulk
+//    copies (cp.async.bulk shared::cta -> shared::cluster) that complete on the RECEIVER's mbarrier, and every
+//    thread of the cluster waits on its own CTA's mbarrier instead of a cluster barrier.  The row scales (f, 1/f)
+//    live with the owner of the position's tile row.  (Measured with clock64, tests/scratch/t4prof.py: the 48 st.shared::cluster.v2 per pivot thread of
 //    the first version cost 44 cycles each -- 2100 of the 2900 cycles of the pivot phase -- and the
 //    MEMBAR.ALL.GPU of the release barrier behind them another 1100.)
-//  * E in the registers of four SMs: CTA r owns positions 64r .. 64r+63; the rows next to a CTA
-//    boundary are read from the neighbour's buffer (ld.shared::cluster);
+//  * E in the registers of four SMs: CTA r owns positions 64r .. 64r+63; the rows next to a CTA boundary are
+//    pushed into the neighbour's buffer (st.shared::cluster) after the pattern-A step;
 //  * per block step (= two rotation steps): one mbarrier wait (pivots published) and one cluster barrier with
 //    release/acquire (tiles and eigenvector rows done).
 #pragma once
@@ -213,9 +214,8 @@ __device__ __forceinline__ void cl4_diag(const Cl4Ctx<T>& cx, int J) {
 
 // ---- off-diagonal tiles owned by this CTA, and in pattern B its strips
 template <typename T, int MODE>
-__device__ __forceinline__ bool cl4_tiles(const Cl4Ctx<T>& cx) {     // returns: this thread wrote another CTA's memory
+__device__ __forceinline__ void cl4_tiles(const Cl4Ctx<T>& cx) {
   using Sh = Cl4Shape;
-  bool wrote_remote = false;
   using T2 = typename Pair2<T>::type;
   constexpr int OFF = (MODE == 1) ? 2 : 0;
   constexpr int W = Sh::kW;
@@ -227,7 +227,6 @@ __device__ __forceinline__ bool cl4_tiles(const Cl4Ctx<T>& cx) {     // returns:
     const int P = (ent >> 16) & 0x3f, Q = (ent >> 22) & 0x3f;
     T* B = cx.M + (ent & 0xffffu);
     const bool remote = (MODE == 1) && (ent >> 28) != 0;
-    wrote_remote = remote;
     const unsigned rb = remote ? cluster_map(cx.m_u32 + (unsigned)(Sh::toff(P + 1, Q) * esz), (unsigned)Sh::owner_row(P + 1)) : 0u;
     T t[16];
     const T2* csP = cx.cs() + Sh::kRec * P;
@@ -324,7 +323,6 @@ __device__ __forceinline__ bool cl4_tiles(const Cl4Ctx<T>& cx) {     // returns:
         const int Qc = cx.nbp - 1;
         T* S = cx.M + Sh::toff(j, Qc) + 2;   // tile (j, Qc), column 2
         const bool remote = Sh::owner_row(j + 1) != cx.rank;
-        wrote_remote = wrote_remote || remote;
         const unsigned rb = remote ? cluster_map(cx.m_u32 + (unsigned)((Sh::toff(j + 1, Qc) + 2) * esz), (unsigned)Sh::owner_row(j + 1)) : 0u;
         // k = 0,1: rows 2,3 of tile (j, Qc); k = 2,3: rows 0,1 of tile (j+1, Qc)
         T a0 = S[8], a1 = S[12], b0 = S[9], b1 = S[13];
@@ -343,7 +341,6 @@ __device__ __forceinline__ bool cl4_tiles(const Cl4Ctx<T>& cx) {     // returns:
       }
     }
   }
-  return wrote_remote;
 }
 
 // ---- eigenvector rows of a block step of mode MODE (see cta4_evecs); the rows next to a CTA boundary come
