@@ -25,14 +25,14 @@
 //    reference's test -- the same stopping rule as the other tiers.  The host reads one flag
 //    per sweep (the call therefore synchronises its stream once per outer sweep).
 #pragma once
+#include <type_traits>
 #include "jpd_common.cuh"
 
 namespace jpd {
 
 constexpr int kBjBlock = 32;          // indices per block
 constexpr int kBjPivot = 64;          // pivot matrix = two blocks
-constexpr int kBjLd = 66;             // shared-memory row pitch (elements): 16-byte aligned rows,
-                                      // rows r and r+4 in different banks
+constexpr int kBjLd = 68;             // shared-memory row pitch (elements): rows 16-byte aligned in fp32 and fp64
 constexpr int kBjThreads = 256;
 
 #if defined(__CUDACC__)
@@ -79,16 +79,23 @@ blk_gather_kernel(const T* __restrict__ Mw, T* __restrict__ P, const int2* __res
   }
 }
 
-// C(4x4 per thread) += A(rows 4ty.., all l) * B(all l, cols 4tx..); A, B in shared memory, pitch kBjLd
+// C += A B for one 64 x 64 x 64 product, 4 x 4 outputs per thread: rows 4ty .. 4ty+3, columns tx, tx+16, tx+32, tx+48.
+// At = A TRANSPOSED in shared memory (At[l][row]), B row-major (B[l][col]), pitch kBjLd.  Per l a thread fetches
+// its four a's as one 32-byte (fp64) / 16-byte (fp32) vector -- the two row groups of a warp make it one wavefront
+// -- and its four b's from four runs of 16 consecutive elements (one wavefront each, the same for both halves of
+// the warp): 6 shared-memory wavefronts per 16 FMAs.  (First version: a's from four rows, b's at a stride of four
+// elements: 20 wavefronts, 40 % of them bank conflicts, FP64 pipe 23 % busy -- profiles/r2_ncu/r2_n512_apply.txt.)
 template <typename T>
-__device__ __forceinline__ void bj_gemm_64(const T* __restrict__ A, const T* __restrict__ B, int ty, int tx, T (&c)[4][4]) {
+__device__ __forceinline__ void bj_gemm_64(const T* __restrict__ At, const T* __restrict__ B, int ty, int tx, T (&c)[4][4]) {
+  using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
 #pragma unroll 8
   for (int l = 0; l < kBjPivot; ++l) {
     T a[4], b[4];
+    const T2 a01 = *reinterpret_cast<const T2*>(At + l * kBjLd + 4 * ty);
+    const T2 a23 = *reinterpret_cast<const T2*>(At + l * kBjLd + 4 * ty + 2);
+    a[0] = a01.x; a[1] = a01.y; a[2] = a23.x; a[3] = a23.y;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = A[(4 * ty + i) * kBjLd + l];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = B[l * kBjLd + 4 * tx + j];
+    for (int j = 0; j < 4; ++j) b[j] = B[l * kBjLd + tx + 16 * j];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -106,9 +113,9 @@ template <typename T>
 __global__ void __launch_bounds__(kBjThreads, 2)
 blk_orthonormalize_kernel(T* __restrict__ Q) {
   extern __shared__ __align__(16) unsigned char bj_smem_raw[];
-  T* sQ = reinterpret_cast<T*>(bj_smem_raw);        // Q row-major: A operand of Q Q^T, B operand of R Q
-  T* sR = sQ + kBjPivot * kBjLd;                    // R = I - Q Q^T (A operand)
-  T* sQt = sR + kBjPivot * kBjLd;                   // Q^T (B operand)
+  T* sQ = reinterpret_cast<T*>(bj_smem_raw);        // Q row-major: B operand of R Q
+  T* sRt = sQ + kBjPivot * kBjLd;                   // R = (I - Q Q^T) / 2, transposed (A operand)
+  T* sQt = sRt + kBjPivot * kBjLd;                  // Q^T row-major = Q transposed: A and B operand of Q Q^T
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   T* q = Q + (size_t)blockIdx.x * (kBjPivot * kBjPivot);
   for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjThreads) {
@@ -123,21 +130,21 @@ blk_orthonormalize_kernel(T* __restrict__ Q) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
-  bj_gemm_64(sQ, sQt, ty, tx, acc);                 // G = Q Q^T
+  bj_gemm_64(sQt, sQt, ty, tx, acc);                // G = Q Q^T
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int r = 4 * ty + i, c = 4 * tx + j;
-      sR[r * kBjLd + c] = T(0.5) * ((r == c ? T(1) : T(0)) - acc[i][j]);
-      acc[i][j] = sQ[r * kBjLd + c];                // Q + (R/2) Q
+      const int r = 4 * ty + i, c = tx + 16 * j;
+      sRt[c * kBjLd + r] = T(0.5) * ((r == c ? T(1) : T(0)) - acc[i][j]);
+      acc[i][j] = sQ[r * kBjLd + c];                // Q + R Q
     }
   __syncthreads();
-  bj_gemm_64(sR, sQ, ty, tx, acc);
+  bj_gemm_64(sRt, sQ, ty, tx, acc);
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) q[(4 * ty + i) * kBjPivot + 4 * tx + j] = acc[i][j];
+    for (int j = 0; j < 4; ++j) q[(4 * ty + i) * kBjPivot + tx + 16 * j] = acc[i][j];
 }
 
 // ---- ApplyRot + ApplyRotLeft of one outer step.  Work items (blockIdx.x) per matrix:
@@ -149,8 +156,8 @@ __global__ void __launch_bounds__(kBjThreads, 2)
 blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q,
                  const int2* __restrict__ pairs, int npairs, int np) {
   extern __shared__ __align__(16) unsigned char bj_smem_raw[];
-  T* sQa = reinterpret_cast<T*>(bj_smem_raw);      // Q_k, row-major (A operand)
-  T* sX = sQa + kBjPivot * kBjLd;                    // the tile (B operand), later T = Q_k X (A operand)
+  T* sQat = reinterpret_cast<T*>(bj_smem_raw);     // Q_k transposed (A operand)
+  T* sX = sQat + kBjPivot * kBjLd;                   // the tile (B operand), later T = Q_k X transposed (A operand)
   T* sQbt = sX + kBjPivot * kBjLd;                   // Q_l^T (B operand)
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int lb = blockIdx.y;
@@ -167,7 +174,7 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
     const int2 pk = pairs[k], pl = pairs[l];
     for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjThreads) {
       const int r = idx >> 6, c = idx & 63;
-      sQa[r * kBjLd + c] = Qb[(size_t)k * 4096 + idx];
+      sQat[c * kBjLd + r] = Qb[(size_t)k * 4096 + idx];                       // transposed
       sQbt[c * kBjLd + r] = Qb[(size_t)l * 4096 + idx];                       // transposed
       sX[r * kBjLd + c] = M[(size_t)bj_row(pk.x, pk.y, r) * np + bj_row(pl.x, pl.y, c)];
     }
@@ -177,12 +184,12 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
-    bj_gemm_64(sQa, sX, ty, tx, acc);                 // T = Q_k X
+    bj_gemm_64(sQat, sX, ty, tx, acc);                // T = Q_k X
     __syncthreads();                                   // every thread has read X
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { sX[(4 * ty + i) * kBjLd + 4 * tx + j] = acc[i][j]; acc[i][j] = T(0); }
+      for (int j = 0; j < 4; ++j) { sX[(tx + 16 * j) * kBjLd + 4 * ty + i] = acc[i][j]; acc[i][j] = T(0); }   // T transposed
     __syncthreads();
     bj_gemm_64(sX, sQbt, ty, tx, acc);                // T Q_l^T
 #pragma unroll
@@ -190,7 +197,7 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
       const int gr = bj_row(pk.x, pk.y, 4 * ty + i);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int gc = bj_row(pl.x, pl.y, 4 * tx + j);
+        const int gc = bj_row(pl.x, pl.y, tx + 16 * j);
         M[(size_t)gr * np + gc] = acc[i][j];
         if (k != l) M[(size_t)gc * np + gr] = acc[i][j];    // the matrix stays symmetric bit for bit
       }
@@ -214,7 +221,7 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
     T* E = Ew + (size_t)lb * np * np;
     for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjThreads) {
       const int r = idx >> 6, c = idx & 63;
-      sQa[r * kBjLd + c] = Qb[(size_t)k * 4096 + idx];
+      sQat[c * kBjLd + r] = Qb[(size_t)k * 4096 + idx];                       // transposed
       sX[r * kBjLd + c] = E[(size_t)bj_row(pk.x, pk.y, r) * np + cb * kBjPivot + c];
     }
     __syncthreads();
@@ -223,12 +230,12 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
-    bj_gemm_64(sQa, sX, ty, tx, acc);
+    bj_gemm_64(sQat, sX, ty, tx, acc);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int gr = bj_row(pk.x, pk.y, 4 * ty + i);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) E[(size_t)gr * np + cb * kBjPivot + 4 * tx + j] = acc[i][j];
+      for (int j = 0; j < 4; ++j) E[(size_t)gr * np + cb * kBjPivot + tx + 16 * j] = acc[i][j];
     }
   }
 }
