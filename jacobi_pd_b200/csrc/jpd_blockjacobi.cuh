@@ -79,6 +79,27 @@ blk_gather_kernel(const T* __restrict__ Mw, T* __restrict__ P, const int2* __res
   }
 }
 
+// 16-byte asynchronous copies global -> shared (LDGSTS): a 64-element row in 64 * sizeof(T) / 16 pieces
+__device__ __forceinline__ void bj_cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void bj_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bj_cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// a 64 x 64 block with row pitch `src_pitch` whose 64 columns are two runs of 32 (at col0 and col1) -> shared memory,
+// row-major with pitch kBjLd; row r of the block is source row rowmap(r)
+template <typename T, typename RowMap>
+__device__ __forceinline__ void bj_load_block_async(T* __restrict__ dst, const T* __restrict__ src, size_t src_pitch,
+                                                    int col0, int col1, RowMap rowmap) {
+  constexpr int kPer = 16 / (int)sizeof(T);             // elements per piece
+  constexpr int kPieces = kBjPivot / kPer;              // pieces per row
+  for (int idx = threadIdx.x; idx < kBjPivot * kPieces; idx += kBjThreads) {
+    const int r = idx / kPieces, c = (idx - r * kPieces) * kPer;
+    const int gc = c < kBjBlock ? col0 + c : col1 + (c - kBjBlock);
+    bj_cp_async16(dst + r * kBjLd + c, src + (size_t)rowmap(r) * src_pitch + gc);
+  }
+}
+
 // C += A B for one 64 x 64 x 64 product, 4 x 4 outputs per thread: rows 4ty .. 4ty+3, columns tx, tx+16, tx+32, tx+48.
 // At = A TRANSPOSED in shared memory (At[l][row]), B row-major (B[l][col]), pitch kBjLd.  Per l a thread fetches
 // its four a's as one 32-byte (fp64) / 16-byte (fp32) vector -- the two row groups of a warp make it one wavefront
@@ -141,19 +162,25 @@ blk_orthonormalize_kernel(T* __restrict__ Q) {
     }
   __syncthreads();
   bj_gemm_64(sRt, sQ, ty, tx, acc);
+  // the result leaves TRANSPOSED (blk_apply wants Q_k^T as the A operand of Q_k X and Q_l^T as the B operand of
+  // (Q_k X) Q_l^T: both become plain row-major copies there), staged through sQt for coalesced stores
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) q[(4 * ty + i) * kBjPivot + tx + 16 * j] = acc[i][j];
+    for (int j = 0; j < 4; ++j) sQt[(tx + 16 * j) * kBjLd + 4 * ty + i] = acc[i][j];      // free since the first product
+  __syncthreads();
+  for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjThreads) q[idx] = sQt[(idx >> 6) * kBjLd + (idx & 63)];
 }
 
 // ---- ApplyRot + ApplyRotLeft of one outer step.  Work items (blockIdx.x) per matrix:
 //   [0, ntile)          tile (k <= l) of M:  M[R_k, R_l] <- Q_k M[R_k, R_l] Q_l^T, and its mirror image
 //   [ntile, ntile + npairs * ncol)   (k, col block c) of E:  E[R_k, C_c] <- Q_k E[R_k, C_c]
-// Q_k = eigenvector ROWS of pivot solve k (row a = new index a).
+// Q_k = eigenvector ROWS of pivot solve k (row a = new index a); Qt holds the blocks TRANSPOSED
+// (blk_orthonormalize_kernel), so both operands that involve Q are plain row-major copies.  All three operands
+// arrive as 16-byte asynchronous copies; Q_l^T, which only the second product needs, lands during the first.
 template <typename T, bool EVECS>
 __global__ void __launch_bounds__(kBjThreads, 2)
-blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q,
+blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Qt,
                  const int2* __restrict__ pairs, int npairs, int np) {
   extern __shared__ __align__(16) unsigned char bj_smem_raw[];
   T* sQat = reinterpret_cast<T*>(bj_smem_raw);     // Q_k transposed (A operand)
@@ -164,7 +191,8 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
   const int ntile = npairs * (npairs + 1) / 2;
   const int item = blockIdx.x;
   T* M = Mw + (size_t)lb * np * np;
-  const T* Qb = Q + (size_t)lb * npairs * (kBjPivot * kBjPivot);
+  const T* Qb = Qt + (size_t)lb * npairs * (kBjPivot * kBjPivot);
+  auto same_row = [](int r) { return r; };
 
   if (item < ntile) {
     // (k, l), k <= l, from the linear index
@@ -172,12 +200,13 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
     while (rest >= npairs - k) { rest -= npairs - k; ++k; }
     const int l = k + rest;
     const int2 pk = pairs[k], pl = pairs[l];
-    for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjThreads) {
-      const int r = idx >> 6, c = idx & 63;
-      sQat[c * kBjLd + r] = Qb[(size_t)k * 4096 + idx];                       // transposed
-      sQbt[c * kBjLd + r] = Qb[(size_t)l * 4096 + idx];                       // transposed
-      sX[r * kBjLd + c] = M[(size_t)bj_row(pk.x, pk.y, r) * np + bj_row(pl.x, pl.y, c)];
-    }
+    bj_load_block_async(sQat, Qb + (size_t)k * 4096, kBjPivot, 0, kBjBlock, same_row);
+    bj_load_block_async(sX, M, (size_t)np, bj_row(pl.x, pl.y, 0), bj_row(pl.x, pl.y, kBjBlock),
+                        [&](int r) { return bj_row(pk.x, pk.y, r); });
+    bj_cp_commit();
+    bj_load_block_async(sQbt, Qb + (size_t)l * 4096, kBjPivot, 0, kBjBlock, same_row);
+    bj_cp_commit();
+    bj_cp_wait<1>();                                   // Q_k^T and the tile are here
     __syncthreads();
     T acc[4][4];
 #pragma unroll
@@ -190,6 +219,7 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) { sX[(tx + 16 * j) * kBjLd + 4 * ty + i] = acc[i][j]; acc[i][j] = T(0); }   // T transposed
+    bj_cp_wait<0>();                                   // Q_l^T
     __syncthreads();
     bj_gemm_64(sX, sQbt, ty, tx, acc);                // T Q_l^T
 #pragma unroll
@@ -219,11 +249,11 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
     const int k = e_item / ncol, cb = e_item - k * ncol;
     const int2 pk = pairs[k];
     T* E = Ew + (size_t)lb * np * np;
-    for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjThreads) {
-      const int r = idx >> 6, c = idx & 63;
-      sQat[c * kBjLd + r] = Qb[(size_t)k * 4096 + idx];                       // transposed
-      sX[r * kBjLd + c] = E[(size_t)bj_row(pk.x, pk.y, r) * np + cb * kBjPivot + c];
-    }
+    bj_load_block_async(sQat, Qb + (size_t)k * 4096, kBjPivot, 0, kBjBlock, same_row);
+    bj_load_block_async(sX, E, (size_t)np, cb * kBjPivot, cb * kBjPivot + kBjBlock,
+                        [&](int r) { return bj_row(pk.x, pk.y, r); });
+    bj_cp_commit();
+    bj_cp_wait<0>();
     __syncthreads();
     T acc[4][4];
 #pragma unroll
