@@ -226,10 +226,19 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
     for (int i = 0; i < 4; ++i) {
       const int gr = bj_row(pk.x, pk.y, 4 * ty + i);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gc = bj_row(pl.x, pl.y, tx + 16 * j);
-        M[(size_t)gr * np + gc] = acc[i][j];
-        if (k != l) M[(size_t)gc * np + gr] = acc[i][j];    // the matrix stays symmetric bit for bit
+      for (int j = 0; j < 4; ++j) M[(size_t)gr * np + bj_row(pl.x, pl.y, tx + 16 * j)] = acc[i][j];
+    }
+    if (k != l) {
+      // the mirror image (the matrix stays symmetric bit for bit): transposed through shared memory -- sQat is free
+      // since the first product -- so that it leaves in 256-byte runs instead of 4096 scattered 8-byte stores
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sQat[(tx + 16 * j) * kBjLd + 4 * ty + i] = acc[i][j];
+      __syncthreads();
+      for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjThreads) {
+        const int r = idx >> 6, c = idx & 63;
+        M[(size_t)bj_row(pl.x, pl.y, r) * np + bj_row(pk.x, pk.y, c)] = sQat[r * kBjLd + c];
       }
     }
     if (k == l) {
