@@ -33,7 +33,9 @@ namespace jpd {
 constexpr int kBjBlock = 32;          // indices per block
 constexpr int kBjPivot = 64;          // pivot matrix = two blocks
 constexpr int kBjLd = 68;             // shared-memory row pitch (elements): rows 16-byte aligned in fp32 and fp64
-constexpr int kBjThreads = 256;
+constexpr int kBjThreads = 256;       // gather kernel
+constexpr int kBjTR = 8;              // output rows per thread of the 64 x 64 x 64 products (x 4 columns)
+constexpr int kBjGemmThreads = 16 * (kBjPivot / kBjTR);   // 128
 
 #if defined(__CUDACC__)
 
@@ -93,32 +95,34 @@ __device__ __forceinline__ void bj_load_block_async(T* __restrict__ dst, const T
                                                     int col0, int col1, RowMap rowmap) {
   constexpr int kPer = 16 / (int)sizeof(T);             // elements per piece
   constexpr int kPieces = kBjPivot / kPer;              // pieces per row
-  for (int idx = threadIdx.x; idx < kBjPivot * kPieces; idx += kBjThreads) {
+  for (int idx = threadIdx.x; idx < kBjPivot * kPieces; idx += kBjGemmThreads) {
     const int r = idx / kPieces, c = (idx - r * kPieces) * kPer;
     const int gc = c < kBjBlock ? col0 + c : col1 + (c - kBjBlock);
     bj_cp_async16(dst + r * kBjLd + c, src + (size_t)rowmap(r) * src_pitch + gc);
   }
 }
 
-// C += A B for one 64 x 64 x 64 product, 4 x 4 outputs per thread: rows 4ty .. 4ty+3, columns tx, tx+16, tx+32, tx+48.
-// At = A TRANSPOSED in shared memory (At[l][row]), B row-major (B[l][col]), pitch kBjLd.  Per l a thread fetches
-// its four a's as one 32-byte (fp64) / 16-byte (fp32) vector -- the two row groups of a warp make it one wavefront
-// -- and its four b's from four runs of 16 consecutive elements (one wavefront each, the same for both halves of
-// the warp): 6 shared-memory wavefronts per 16 FMAs.  (First version: a's from four rows, b's at a stride of four
-// elements: 20 wavefronts, 40 % of them bank conflicts, FP64 pipe 23 % busy -- profiles/r2_ncu/r2_n512_apply.txt.)
+// C += A B for one 64 x 64 x 64 product, 8 x 4 outputs per thread (128 threads): rows 8ty .. 8ty+7, columns tx, tx+16,
+// tx+32, tx+48.  At = A TRANSPOSED in shared memory (At[l][row]), B row-major (B[l][col]), pitch kBjLd.  Per l a
+// thread fetches its eight a's as four 16-byte vectors (the same for 16 lanes) and its four b's from four runs of 16
+// consecutive elements: 16 shared-memory wavefronts per 32 FMAs.  History (n = 512, application kernel, ncu):
+// 4 x 4 outputs with a's from four rows and b's at a stride of four elements: 20 wavefronts per 16 FMAs, 40 % of them
+// bank conflicts, FP64 pipe 23 % busy; 4 x 4 with this layout: 12 per 16, FP64 51 %, shared pipe 81 %.
 template <typename T>
-__device__ __forceinline__ void bj_gemm_64(const T* __restrict__ At, const T* __restrict__ B, int ty, int tx, T (&c)[4][4]) {
+__device__ __forceinline__ void bj_gemm_64(const T* __restrict__ At, const T* __restrict__ B, int ty, int tx, T (&c)[kBjTR][4]) {
   using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
 #pragma unroll 8
   for (int l = 0; l < kBjPivot; ++l) {
-    T a[4], b[4];
-    const T2 a01 = *reinterpret_cast<const T2*>(At + l * kBjLd + 4 * ty);
-    const T2 a23 = *reinterpret_cast<const T2*>(At + l * kBjLd + 4 * ty + 2);
-    a[0] = a01.x; a[1] = a01.y; a[2] = a23.x; a[3] = a23.y;
+    T a[kBjTR], b[4];
+#pragma unroll
+    for (int i = 0; i < kBjTR; i += 2) {
+      const T2 v = *reinterpret_cast<const T2*>(At + l * kBjLd + kBjTR * ty + i);
+      a[i] = v.x; a[i + 1] = v.y;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) b[j] = B[l * kBjLd + tx + 16 * j];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < kBjTR; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) c[i][j] = jfma(a[i], b[j], c[i][j]);
   }
@@ -131,7 +135,7 @@ __device__ __forceinline__ void bj_gemm_64(const T* __restrict__ At, const T* __
 // 5e-5 at n = 257 in fp32 -- at and beyond the north-star tolerance).  One step squares the
 // defect; it costs two 64^3 products per pivot, a few percent of the application.
 template <typename T>
-__global__ void __launch_bounds__(kBjThreads, 2)
+__global__ void __launch_bounds__(kBjGemmThreads, 2)
 blk_orthonormalize_kernel(T* __restrict__ Q) {
   extern __shared__ __align__(16) unsigned char bj_smem_raw[];
   T* sQ = reinterpret_cast<T*>(bj_smem_raw);        // Q row-major: B operand of R Q
@@ -139,24 +143,24 @@ blk_orthonormalize_kernel(T* __restrict__ Q) {
   T* sQt = sRt + kBjPivot * kBjLd;                  // Q^T row-major = Q transposed: A and B operand of Q Q^T
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   T* q = Q + (size_t)blockIdx.x * (kBjPivot * kBjPivot);
-  for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjThreads) {
+  for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjGemmThreads) {
     const int r = idx >> 6, c = idx & 63;
     const T v = q[idx];
     sQ[r * kBjLd + c] = v;
     sQt[c * kBjLd + r] = v;
   }
   __syncthreads();
-  T acc[4][4];
+  T acc[kBjTR][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < kBjTR; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
   bj_gemm_64(sQt, sQt, ty, tx, acc);                // G = Q Q^T
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < kBjTR; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int r = 4 * ty + i, c = tx + 16 * j;
+      const int r = kBjTR * ty + i, c = tx + 16 * j;
       sRt[c * kBjLd + r] = T(0.5) * ((r == c ? T(1) : T(0)) - acc[i][j]);
       acc[i][j] = sQ[r * kBjLd + c];                // Q + R Q
     }
@@ -165,11 +169,11 @@ blk_orthonormalize_kernel(T* __restrict__ Q) {
   // the result leaves TRANSPOSED (blk_apply wants Q_k^T as the A operand of Q_k X and Q_l^T as the B operand of
   // (Q_k X) Q_l^T: both become plain row-major copies there), staged through sQt for coalesced stores
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < kBjTR; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) sQt[(tx + 16 * j) * kBjLd + 4 * ty + i] = acc[i][j];      // free since the first product
+    for (int j = 0; j < 4; ++j) sQt[(tx + 16 * j) * kBjLd + kBjTR * ty + i] = acc[i][j];      // free since the first product
   __syncthreads();
-  for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjThreads) q[idx] = sQt[(idx >> 6) * kBjLd + (idx & 63)];
+  for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjGemmThreads) q[idx] = sQt[(idx >> 6) * kBjLd + (idx & 63)];
 }
 
 // ---- ApplyRot + ApplyRotLeft of one outer step.  Work items (blockIdx.x) per matrix:
@@ -179,7 +183,7 @@ blk_orthonormalize_kernel(T* __restrict__ Q) {
 // (blk_orthonormalize_kernel), so both operands that involve Q are plain row-major copies.  All three operands
 // arrive as 16-byte asynchronous copies; Q_l^T, which only the second product needs, lands during the first.
 template <typename T, bool EVECS>
-__global__ void __launch_bounds__(kBjThreads, 2)
+__global__ void __launch_bounds__(kBjGemmThreads, 2)
 blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Qt,
                  const int2* __restrict__ pairs, int npairs, int np) {
   extern __shared__ __align__(16) unsigned char bj_smem_raw[];
@@ -208,23 +212,23 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
     bj_cp_commit();
     bj_cp_wait<1>();                                   // Q_k^T and the tile are here
     __syncthreads();
-    T acc[4][4];
+    T acc[kBjTR][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < kBjTR; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
     bj_gemm_64(sQat, sX, ty, tx, acc);                // T = Q_k X
     __syncthreads();                                   // every thread has read X
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < kBjTR; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { sX[(tx + 16 * j) * kBjLd + 4 * ty + i] = acc[i][j]; acc[i][j] = T(0); }   // T transposed
+      for (int j = 0; j < 4; ++j) { sX[(tx + 16 * j) * kBjLd + kBjTR * ty + i] = acc[i][j]; acc[i][j] = T(0); }   // T transposed
     bj_cp_wait<0>();                                   // Q_l^T
     __syncthreads();
     bj_gemm_64(sX, sQbt, ty, tx, acc);                // T Q_l^T
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int gr = bj_row(pk.x, pk.y, 4 * ty + i);
+    for (int i = 0; i < kBjTR; ++i) {
+      const int gr = bj_row(pk.x, pk.y, kBjTR * ty + i);
 #pragma unroll
       for (int j = 0; j < 4; ++j) M[(size_t)gr * np + bj_row(pl.x, pl.y, tx + 16 * j)] = acc[i][j];
     }
@@ -232,11 +236,11 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
       // the mirror image (the matrix stays symmetric bit for bit): transposed through shared memory -- sQat is free
       // since the first product -- so that it leaves in 256-byte runs instead of 4096 scattered 8-byte stores
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < kBjTR; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sQat[(tx + 16 * j) * kBjLd + 4 * ty + i] = acc[i][j];
+        for (int j = 0; j < 4; ++j) sQat[(tx + 16 * j) * kBjLd + kBjTR * ty + i] = acc[i][j];
       __syncthreads();
-      for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjThreads) {
+      for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjGemmThreads) {
         const int r = idx >> 6, c = idx & 63;
         M[(size_t)bj_row(pl.x, pl.y, r) * np + bj_row(pk.x, pk.y, c)] = sQat[r * kBjLd + c];
       }
@@ -244,7 +248,7 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
     if (k == l) {
       // symmetrise the diagonal tile's two triangles (Q P Q^T is symmetric only up to rounding)
       __syncthreads();
-      for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjThreads) {
+      for (int idx = tid; idx < kBjPivot * kBjPivot; idx += kBjGemmThreads) {
         const int r = idx >> 6, c = idx & 63;
         if (r > c) {
           const int gr = bj_row(pk.x, pk.y, r), gc = bj_row(pk.x, pk.y, c);
@@ -264,15 +268,15 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
     bj_cp_commit();
     bj_cp_wait<0>();
     __syncthreads();
-    T acc[4][4];
+    T acc[kBjTR][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < kBjTR; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
     bj_gemm_64(sQat, sX, ty, tx, acc);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int gr = bj_row(pk.x, pk.y, 4 * ty + i);
+    for (int i = 0; i < kBjTR; ++i) {
+      const int gr = bj_row(pk.x, pk.y, kBjTR * ty + i);
 #pragma unroll
       for (int j = 0; j < 4; ++j) E[(size_t)gr * np + cb * kBjPivot + tx + 16 * j] = acc[i][j];
     }

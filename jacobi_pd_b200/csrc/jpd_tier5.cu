@@ -117,8 +117,8 @@ int launch_block(const T* mat, T* evals, T* evecs, int* iters, int n, long long 
         status = launch_tier3<T>(P, pev, Q, piv_it, kBjPivot, (long long)npairs * cnt, JPD_LAYOUT_AOS,
                                  JPD_SORT_DECREASING_EVALS, 1, -inner_sweeps(), st);
         if (status != JPD_OK) break;
-        blk_orthonormalize_kernel<T><<<(unsigned)(npairs * cnt), kBjThreads, apply_smem, st>>>(Q);
-        apply<<<dim3(items, (unsigned)cnt), kBjThreads, apply_smem, st>>>(Mw, Ew, Q, prs, npairs, np);
+        blk_orthonormalize_kernel<T><<<(unsigned)(npairs * cnt), kBjGemmThreads, apply_smem, st>>>(Q);
+        apply<<<dim3(items, (unsigned)cnt), kBjGemmThreads, apply_smem, st>>>(Mw, Ew, Q, prs, npairs, np);
         blk_count_kernel<<<cb, 128, 0, st>>>(piv_it, npairs, cnt, rot_total, rot_sweep, any_left);
         g_launches.fetch_add(4, std::memory_order_relaxed);
       }
