@@ -33,6 +33,9 @@ namespace jpd {
 constexpr int kBjBlock = 32;          // indices per block
 constexpr int kBjPivot = 64;          // pivot matrix = two blocks
 constexpr int kBjLd = 68;             // shared-memory row pitch (elements): rows 16-byte aligned in fp32 and fp64
+#ifndef JPD_BJ_APPLY_BUFFERS
+#define JPD_BJ_APPLY_BUFFERS 2   // measured: 2 (three resident blocks per SM) beats 3 (Q_l^T prefetched) by 3-5 %, tests/scratch/t5vv.py
+#endif
 constexpr int kBjThreads = 256;       // gather kernel
 constexpr int kBjTR = 8;              // output rows per thread of the 64 x 64 x 64 products (x 4 columns)
 constexpr int kBjGemmThreads = 16 * (kBjPivot / kBjTR);   // 128
@@ -183,13 +186,15 @@ blk_orthonormalize_kernel(T* __restrict__ Q) {
 // (blk_orthonormalize_kernel), so both operands that involve Q are plain row-major copies.  All three operands
 // arrive as 16-byte asynchronous copies; Q_l^T, which only the second product needs, lands during the first.
 template <typename T, bool EVECS>
-__global__ void __launch_bounds__(kBjGemmThreads, 2)
+__global__ void __launch_bounds__(kBjGemmThreads, JPD_BJ_APPLY_BUFFERS == 2 ? 3 : 2)
 blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Qt,
                  const int2* __restrict__ pairs, int npairs, int np) {
   extern __shared__ __align__(16) unsigned char bj_smem_raw[];
   T* sQat = reinterpret_cast<T*>(bj_smem_raw);     // Q_k transposed (A operand)
   T* sX = sQat + kBjPivot * kBjLd;                   // the tile (B operand), later T = Q_k X transposed (A operand)
-  T* sQbt = sX + kBjPivot * kBjLd;                   // Q_l^T (B operand)
+  // Q_l^T (B operand of the second product): a third buffer that fills during the first product, or -- two buffers,
+  // three resident blocks per SM instead of two -- Q_k^T's buffer once the first product is done
+  T* sQbt = JPD_BJ_APPLY_BUFFERS == 2 ? sQat : sX + kBjPivot * kBjLd;
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int lb = blockIdx.y;
   const int ntile = npairs * (npairs + 1) / 2;
@@ -208,7 +213,7 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
     bj_load_block_async(sX, M, (size_t)np, bj_row(pl.x, pl.y, 0), bj_row(pl.x, pl.y, kBjBlock),
                         [&](int r) { return bj_row(pk.x, pk.y, r); });
     bj_cp_commit();
-    bj_load_block_async(sQbt, Qb + (size_t)l * 4096, kBjPivot, 0, kBjBlock, same_row);
+    if (JPD_BJ_APPLY_BUFFERS != 2) bj_load_block_async(sQbt, Qb + (size_t)l * 4096, kBjPivot, 0, kBjBlock, same_row);
     bj_cp_commit();
     bj_cp_wait<1>();                                   // Q_k^T and the tile are here
     __syncthreads();
@@ -218,7 +223,8 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
     bj_gemm_64(sQat, sX, ty, tx, acc);                // T = Q_k X
-    __syncthreads();                                   // every thread has read X
+    __syncthreads();                                   // every thread has read X (and Q_k^T)
+    if (JPD_BJ_APPLY_BUFFERS == 2) { bj_load_block_async(sQbt, Qb + (size_t)l * 4096, kBjPivot, 0, kBjBlock, same_row); bj_cp_commit(); }
 #pragma unroll
     for (int i = 0; i < kBjTR; ++i)
 #pragma unroll
@@ -235,6 +241,7 @@ blk_apply_kernel(T* __restrict__ Mw, T* __restrict__ Ew, const T* __restrict__ Q
     if (k != l) {
       // the mirror image (the matrix stays symmetric bit for bit): transposed through shared memory -- sQat is free
       // since the first product -- so that it leaves in 256-byte runs instead of 4096 scattered 8-byte stores
+      if (JPD_BJ_APPLY_BUFFERS == 2) __syncthreads();  // ... with two buffers: since the second product
 #pragma unroll
       for (int i = 0; i < kBjTR; ++i)
 #pragma unroll

@@ -88,10 +88,11 @@ int launch_block(const T* mat, T* evals, T* evecs, int* iters, int n, long long 
     }
     BJ_TRY(cudaMemcpyAsync(d_pairs, h_pairs, sizeof(int2) * npairs * nsteps, cudaMemcpyHostToDevice, st));
   }
-  const size_t apply_smem = sizeof(T) * 3 * kBjPivot * kBjLd;
+  const size_t ortho_smem = sizeof(T) * 3 * kBjPivot * kBjLd;
+  const size_t apply_smem = sizeof(T) * JPD_BJ_APPLY_BUFFERS * kBjPivot * kBjLd;
   auto apply = calc ? blk_apply_kernel<T, true> : blk_apply_kernel<T, true>;   // E is always kept: it marks the padding rows
   BJ_TRY(cudaFuncSetAttribute(apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem));
-  BJ_TRY(cudaFuncSetAttribute(blk_orthonormalize_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem));
+  BJ_TRY(cudaFuncSetAttribute(blk_orthonormalize_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ortho_smem));
   const int ntile = npairs * (npairs + 1) / 2;
   const int items = ntile + npairs * (np / kBjPivot);
 
@@ -117,7 +118,7 @@ int launch_block(const T* mat, T* evals, T* evecs, int* iters, int n, long long 
         status = launch_tier3<T>(P, pev, Q, piv_it, kBjPivot, (long long)npairs * cnt, JPD_LAYOUT_AOS,
                                  JPD_SORT_DECREASING_EVALS, 1, -inner_sweeps(), st);
         if (status != JPD_OK) break;
-        blk_orthonormalize_kernel<T><<<(unsigned)(npairs * cnt), kBjGemmThreads, apply_smem, st>>>(Q);
+        blk_orthonormalize_kernel<T><<<(unsigned)(npairs * cnt), kBjGemmThreads, ortho_smem, st>>>(Q);
         apply<<<dim3(items, (unsigned)cnt), kBjGemmThreads, apply_smem, st>>>(Mw, Ew, Q, prs, npairs, np);
         blk_count_kernel<<<cb, 128, 0, st>>>(piv_it, npairs, cnt, rot_total, rot_sweep, any_left);
         g_launches.fetch_add(4, std::memory_order_relaxed);
